@@ -1,0 +1,79 @@
+"""Whole-model CPU oracle for PiT -- TEST INFRASTRUCTURE ONLY (see posatt_oracle.py header).
+
+Functional restatement of ``pit.encoder / processor / decoder`` (pit.py:108-127) and of the
+``forward`` methods the experiment scripts wrap around them, driven by a plain
+``state_dict`` whose keys are the reference's (``down.lmda``, ``en_layer.mlp1.weight`` ...).
+Every position-attention stage goes through the dense formulation of
+``posatt_oracle`` (quantile + softmax + einsum on materialised N x M tensors), i.e. the
+reference's own CPU cost profile -- which is why ``bench.py`` may time it as ``cpu_baseline``.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+from . import posatt_oracle as po
+
+Params = Dict[str, torch.Tensor]
+
+
+def two_layer(p: Params, name: str, x: torch.Tensor) -> torch.Tensor:
+    """kaiming_mlp.forward (pit.py:21-26): Linear -> exact GELU -> Linear."""
+    x = F.linear(x, p[f"{name}.mlp1.weight"], p[f"{name}.mlp1.bias"])
+    return F.linear(F.gelu(x), p[f"{name}.mlp2.weight"], p[f"{name}.mlp2.bias"])
+
+
+def encode(p: Params, variant, mesh_in, func_in, mesh_ltt, en_loc):
+    """pit.encoder (pit.py:108-112)."""
+    z = po.dense_posatt(mesh_ltt, mesh_in, func_in, p["down.lmda"], en_loc, variant)
+    return F.gelu(two_layer(p, "en_layer", z))
+
+
+def process(p: Params, variant, func_ltt, mesh_ltt, n_blocks):
+    """pit.processor (pit.py:114-122): self stage with concat, locality fixed at 1.0 (pit.py:102)."""
+    for i in range(n_blocks):
+        z = po.dense_posatt(mesh_ltt, mesh_ltt, func_ltt, p[f"conv.{i}.lmda"], 1.0, variant, self_concat=True)
+        func_ltt = F.gelu(two_layer(p, f"mlp.{i}", z))
+    return func_ltt
+
+
+def decode(p: Params, variant, mesh_ltt, func_ltt, mesh_out, de_loc):
+    """pit.decoder (pit.py:124-127)."""
+    z = po.dense_posatt(mesh_out, mesh_ltt, func_ltt, p["up.lmda"], de_loc, variant)
+    return two_layer(p, "de", z)
+
+
+def n_blocks_of(p: Params) -> int:
+    return 1 + max(int(k.split(".")[1]) for k in p if k.startswith("conv."))
+
+
+def forward_shared_mesh(p: Params, variant, mesh_in, func_in, mesh_ltt, mesh_out, en_loc, de_loc):
+    """Burgers / Sod / Darcy style forward (train_burgers.py:40-49, train_darcy.py:46-59):
+    the batch shares one mesh; coordinates are prepended to the input features."""
+    sd = mesh_ltt.shape[-1]
+    lead = mesh_out.shape[:-1]
+    mesh_in, mesh_out = mesh_in.reshape(-1, sd), mesh_out.reshape(-1, sd)
+    func_in = func_in.reshape(func_in.shape[0], mesh_in.shape[0], -1)
+    feats = torch.cat((mesh_in.unsqueeze(0).expand(func_in.shape[0], -1, -1), func_in), -1)
+    h = encode(p, variant, mesh_in, feats, mesh_ltt, en_loc)
+    h = process(p, variant, h, mesh_ltt, n_blocks_of(p))
+    out = decode(p, variant, mesh_ltt, h, mesh_out, de_loc)
+    return out.reshape(func_in.shape[0], *lead, -1)
+
+
+def forward_point_cloud(p: Params, mesh_in, func_in, mesh_ltt, mesh_out, en_loc, de_loc):
+    """Elasticity / NACA style forward (train_elasticity.py:41-54, train_naca.py:47-61):
+    every sample carries its own meshes (B,L,sd); features are used as given."""
+    h = encode(p, "euclid", mesh_in, func_in, mesh_ltt, en_loc)
+    h = process(p, "euclid", h, mesh_ltt, n_blocks_of(p))
+    return decode(p, "euclid", mesh_ltt, h, mesh_out, de_loc)
+
+
+def rel_lp_loss(true: torch.Tensor, pred: torch.Tensor, out_dim: int, p: int) -> torch.Tensor:
+    """RelLpNorm (utils.py:80-98): per-sample relative L_p error, mean over variables, SUM over batch."""
+    t = true.reshape(true.shape[0], -1, out_dim)
+    q = pred.reshape(pred.shape[0], -1, out_dim)
+    ratio = torch.norm(t - q, p=p, dim=1) / torch.norm(t, p=p, dim=1)
+    return ratio.mean(-1).sum()
