@@ -1,0 +1,115 @@
+/*
+ * pit_posatt.h -- C ABI of the B200 (sm_100a) position-attention library, libpit_posatt.so.
+ *
+ * Drop-in boundary for the hot path of the Position-induced Transformer reference
+ * (junfeng-chen/position_induced_transformer, file pit.py).  Every entry point replaces a
+ * piece of reference Python that runs on materialised N x M tensors:
+ *
+ *   pit_quantile_ranks      torch.quantile rank arithmetic        pit.py:49, 136, 197, 255
+ *   pit_rowstat             the row sort inside torch.quantile    pit.py:49, 136, 197, 255
+ *   pit_posatt_forward      dist2att + convolution (+ concat)     pit.py:46-57, 133-144, 190-200, 247-258, 37-44
+ *   pit_posatt_backward     what autograd replays for the above   (no explicit code in the reference)
+ *
+ * Conventions
+ *   - all tensors are fp32, contiguous, row-major, resident on the CURRENT CUDA device;
+ *   - pointers are device pointers unless a parameter is documented as host;
+ *   - nothing is allocated, freed or synchronised inside the library: outputs and the
+ *     workspace are caller-owned; kernels are enqueued on `stream` (a cudaStream_t);
+ *   - every function returns PIT_OK (0) or a negative PIT_ERR_* code; pit_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - there is no CPU fallback: without a CUDA device every launch returns PIT_ERR_CUDA.
+ */
+#ifndef PIT_POSATT_H_
+#define PIT_POSATT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIT_ABI_VERSION 1
+
+#define PIT_OK 0
+#define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
+#define PIT_ERR_CUDA (-2)      /* CUDA runtime reported an error (launch, no device, ...) */
+#define PIT_ERR_WORKSPACE (-3) /* caller-provided workspace too small */
+
+/* Distance variants (reference class families). */
+#define PIT_EUCLID 0     /* posatt / posatt_fixed            pit.py:47, 134  */
+#define PIT_PERIODIC1D 1 /* posatt_periodic1d                pit.py:191-195  */
+#define PIT_PERIODIC2D 2 /* posatt_periodic2d                pit.py:248-253  */
+
+/* Problem description shared by all entry points. */
+typedef struct pit_problem {
+  int32_t variant;      /* PIT_EUCLID | PIT_PERIODIC1D | PIT_PERIODIC2D                          */
+  int32_t space_dim;    /* coordinates per point: 1 or 2                                          */
+  int32_t mesh_batched; /* 0: meshes are (N,sd)/(M,sd), shared by the batch (posatt_fixed, ...)   */
+                        /* 1: meshes are (B,N,sd)/(B,M,sd), one per sample   (posatt)             */
+  int32_t batch;        /* B: samples in `values`                                                 */
+  int32_t n_head;       /* H                                                                      */
+  int32_t n_out;        /* N: rows   = points of mesh_out                                         */
+  int32_t n_in;         /* M: columns = points of mesh_in                                         */
+  int32_t dim;          /* D: value features per point                                            */
+} pit_problem_t;
+
+/* Row statistics in squared-distance space (head independent); each array has
+ * (mesh_batched ? B : 1) * N entries. v_lo / v_hi may be NULL for a global stage. */
+typedef struct pit_rowstat {
+  const float* v_min; /* smallest d2 of the row                                     */
+  const float* v_lo;  /* k_lo-th smallest d2 (0-based)                              */
+  const float* v_hi;  /* k_hi-th smallest d2                                        */
+  float weight;       /* interpolation weight w of torch.quantile, in [0,1)        */
+  int32_t masked;     /* 0: locality >= 1, every column kept; 1: apply the quantile mask */
+} pit_rowstat_t;
+
+/* Library identification. */
+int pit_abi_version(void);
+const char* pit_last_error(void);
+/* Number of kernel launches issued by this process through the library so far. */
+uint64_t pit_launch_count(void);
+
+/* Host-side: rank arithmetic of torch.quantile(x, q, dim=-1) with linear interpolation
+ * on a row of m entries: rank = fp32(q) * fp32(m-1); k_lo = floor, k_hi = ceil, w = rank - k_lo. */
+int pit_quantile_ranks(double q, int32_t m, int32_t* k_lo, int32_t* k_hi, float* w);
+
+/* Bytes of scratch pit_rowstat / pit_posatt_forward / pit_posatt_backward may need for `p`. */
+size_t pit_workspace_bytes(const pit_problem_t* p);
+
+/* Per-row order statistics of the squared distances.
+ *   mesh_out  [(B),N,sd]   mesh_in [(B),M,sd]
+ *   period    device pointer to the wrap length l (periodic variants), else NULL
+ *   v_min, v_lo, v_hi  outputs, [(B),N] each                                              */
+int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
+                const float* period, int32_t k_lo, int32_t k_hi,
+                float* v_min, float* v_lo, float* v_hi, void* stream);
+
+/* Fused position-attention forward.
+ *   values [B,M,D]; scale [H] = tan(c*(1+sin(lmda))) (pit.py:48), computed by the caller;
+ *   out: row (b,n) starts at out + ((size_t)b*N + n)*ld_out + col_off and receives H*D floats,
+ *        head-major (h*D + d) -- ld_out = H*D, col_off = 0 for a cross stage;
+ *        ld_out = (1+H)*D, col_off = D for the self stage with concat (the caller, or
+ *        copy_values != 0, fills the first D columns with `values`, which requires N == M);
+ *   rowsum [(B),H,N]: sum of unnormalised weights exp(s*v_min - s*d2) of each row (saved for backward).  */
+int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
+                       const float* period, const float* values, const float* scale,
+                       const pit_rowstat_t* stat, float* out, int64_t ld_out, int64_t col_off,
+                       int32_t copy_values, float* rowsum, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Fused backward.  d_out uses the same (ld_out, col_off) addressing as `out`.
+ *   d_values [B,M,D]  (may be NULL: not computed).  If accumulate_concat != 0 the first D columns
+ *                     of d_out (the concat pass-through, pit.py:44) are added into d_values.
+ *   d_scale_rows [(B),H,N]: per-row contribution to dL/ds_h; dL/ds_h = sum over rows (and batch). May be NULL. */
+int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
+                        const float* period, const float* values, const float* scale,
+                        const pit_rowstat_t* stat, const float* rowsum, const float* d_out,
+                        int64_t ld_out, int64_t col_off, int32_t accumulate_concat,
+                        float* d_values, float* d_scale_rows, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIT_POSATT_H_ */

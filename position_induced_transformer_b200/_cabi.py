@@ -1,0 +1,73 @@
+"""ctypes binding of libpit_posatt.so (C ABI declared in include/pit_posatt.h).
+
+Loading never falls back to anything: if the shared library is missing or fails to load the
+import raises, and every entry point raises RuntimeError on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
+
+PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
+VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
+ABI_VERSION = 1
+
+EXPORTS = (
+    "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
+    "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward",
+)
+
+
+class Problem(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("variant", "space_dim", "mesh_batched", "batch", "n_head", "n_out", "n_in", "dim")]
+
+
+class RowStat(C.Structure):
+    _fields_ = [("v_min", C.c_void_p), ("v_lo", C.c_void_p), ("v_hi", C.c_void_p),
+                ("weight", C.c_float), ("masked", C.c_int32)]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m position_induced_transformer_b200.build` "
+            "(there is no CPU or PyTorch fallback for position-attention)")
+    lib = C.CDLL(LIB_PATH)
+    p, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    lib.pit_abi_version.restype = C.c_int
+    lib.pit_last_error.restype = C.c_char_p
+    lib.pit_launch_count.restype = C.c_uint64
+    lib.pit_quantile_ranks.argtypes = [C.c_double, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]
+    lib.pit_workspace_bytes.argtypes = [C.POINTER(Problem)]
+    lib.pit_workspace_bytes.restype = C.c_size_t
+    lib.pit_rowstat.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, i32, i32, f32p, f32p, f32p, p]
+    lib.pit_posatt_forward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
+                                       f32p, i64, i64, i32, f32p, p, C.c_size_t, p]
+    lib.pit_posatt_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat), f32p,
+                                        f32p, i64, i64, i32, f32p, f32p, p, C.c_size_t, p]
+    if lib.pit_abi_version() != ABI_VERSION:
+        raise ImportError(f"libpit_posatt.so ABI {lib.pit_abi_version()} != expected {ABI_VERSION}; rebuild it")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib.pit_last_error().decode()}")
+
+
+def quantile_ranks(q: float, m: int):
+    """(k_lo, k_hi, w) of torch.quantile(x, q, dim=-1) on rows of m entries."""
+    lo, hi, w = C.c_int32(), C.c_int32(), C.c_float()
+    check(lib.pit_quantile_ranks(float(q), int(m), C.byref(lo), C.byref(hi), C.byref(w)), "pit_quantile_ranks")
+    return lo.value, hi.value, w.value
+
+
+def launch_count() -> int:
+    return int(lib.pit_launch_count())

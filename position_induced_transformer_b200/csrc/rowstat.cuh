@@ -1,0 +1,174 @@
+// K0 rowstat: exact order statistics of the squared distances of every row.
+//
+// Replaces the full row sort inside torch.quantile (pit.py:49, 136, 197, 255): the mask only
+// needs the k_lo-th and k_hi-th smallest d2 of a row (head independent, because multiplying by
+// the positive per-head scale and rounding is monotone) plus the row minimum, which is the
+// soft-max shift.  Selection is a radix select on the fp32 bit pattern (d2 >= +0, so unsigned
+// integer order is numeric order); nothing of size N x M ever reaches HBM.
+//
+// Two mappings:
+//   warp-per-row   M <= 1024: the row's d2 live in registers, 32 one-bit ballot/REDUX steps;
+//   block-per-row  larger M: 4 passes of 8-bit digits with a shared-memory histogram,
+//                  d2 recomputed on every pass from the (L1/L2 resident) coordinates.
+#pragma once
+#include "geometry.cuh"
+
+namespace pit {
+
+struct RowstatParams {
+  const float* mesh_out;
+  const float* mesh_in;
+  const float* period;
+  float* v_min;
+  float* v_lo;
+  float* v_hi;
+  int rows_total;  // (mesh_batched ? B : 1) * N
+  int N, M, sd, mesh_batched;
+  int k_lo, k_hi;
+};
+
+template <int GEO, int R>
+__global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= P.rows_total) return;
+  const int bm = P.mesh_batched ? row / P.N : 0;
+  const float* mesh_in = P.mesh_in + (int64_t)bm * P.M * P.sd;
+  const float period = P.period ? __ldg(P.period) : 0.f;
+  const Point<GEO> o = load_point<GEO>(P.mesh_out, row, P.sd);
+
+  uint32_t key[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int j = r * 32 + lane;
+    key[r] = 0xffffffffu;
+    if (j < P.M) key[r] = __float_as_uint(dist2<GEO>(o, load_point<GEO>(mesh_in, j, P.sd), period));
+  }
+  uint32_t mn = key[0];
+#pragma unroll
+  for (int r = 1; r < R; ++r) mn = min(mn, key[r]);
+  mn = __reduce_min_sync(FULL, mn);
+
+  // k_lo-th smallest key, most significant bit first.
+  uint32_t prefix = 0;
+  int k = P.k_lo;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) c += (((key[r] ^ prefix) >> bit) == 0u) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (k >= c) {
+      k -= c;
+      prefix |= 1u << bit;
+    }
+  }
+  const uint32_t lo = prefix;
+  uint32_t hi = lo;
+  if (P.k_hi != P.k_lo) {  // k_hi == k_lo + 1
+    int le = 0;
+    uint32_t gt = 0xffffffffu;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      le += (key[r] <= lo) ? 1 : 0;
+      if (key[r] > lo) gt = min(gt, key[r]);
+    }
+    le = __reduce_add_sync(FULL, le);
+    gt = __reduce_min_sync(FULL, gt);
+    if (P.k_hi >= le) hi = gt;
+  }
+  if (lane == 0) {
+    P.v_min[row] = __uint_as_float(mn);
+    P.v_lo[row] = __uint_as_float(lo);
+    P.v_hi[row] = __uint_as_float(hi);
+  }
+}
+
+constexpr int ROWSTAT_BLOCK = 256;
+
+template <int GEO>
+__global__ void __launch_bounds__(ROWSTAT_BLOCK) rowstat_block_kernel(const RowstatParams P) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix, s_min, s_gt;
+  __shared__ int s_k, s_le;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int bm = P.mesh_batched ? row / P.N : 0;
+  const float* mesh_in = P.mesh_in + (int64_t)bm * P.M * P.sd;
+  const float period = P.period ? __ldg(P.period) : 0.f;
+  const Point<GEO> o = load_point<GEO>(P.mesh_out, row, P.sd);
+  // Every thread runs the same number of iterations so the warp-wide match below is convergent.
+  const int m_pad = (P.M + ROWSTAT_BLOCK - 1) / ROWSTAT_BLOCK * ROWSTAT_BLOCK;
+
+  if (tid == 0) {
+    s_prefix = 0;
+    s_k = P.k_lo;
+    s_min = 0xffffffffu;
+    s_gt = 0xffffffffu;
+    s_le = 0;
+  }
+  uint32_t my_min = 0xffffffffu;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int j = tid; j < m_pad; j += ROWSTAT_BLOCK) {
+      bool take = j < P.M;
+      uint32_t key = 0;
+      if (take) {
+        key = __float_as_uint(dist2<GEO>(o, load_point<GEO>(mesh_in, j, P.sd), period));
+        if (pass == 0)
+          my_min = min(my_min, key);
+        else
+          take = ((key ^ prefix) >> (shift + 8)) == 0u;
+      }
+      const uint32_t digit = (key >> shift) & 255u;
+      // warp-aggregated histogram update: one atomic per distinct digit in the warp
+      const unsigned active = __ballot_sync(FULL, take);
+      if (take) {
+        const unsigned peers = __match_any_sync(active, digit);
+        if ((__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[digit], __popc(peers));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int k = s_k, cum = 0, d = 0;
+      for (; d < 255; ++d) {
+        if (k < cum + hist[d]) break;
+        cum += hist[d];
+      }
+      s_k = k - cum;
+      s_prefix = prefix | ((uint32_t)d << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t lo = s_prefix;
+  my_min = __reduce_min_sync(FULL, my_min);
+  if ((tid & 31) == 0) atomicMin(&s_min, my_min);
+  if (P.k_hi != P.k_lo) {
+    int le = 0;
+    uint32_t gt = 0xffffffffu;
+    for (int j = tid; j < P.M; j += ROWSTAT_BLOCK) {
+      const uint32_t key = __float_as_uint(dist2<GEO>(o, load_point<GEO>(mesh_in, j, P.sd), period));
+      le += (key <= lo) ? 1 : 0;
+      if (key > lo) gt = min(gt, key);
+    }
+    le = __reduce_add_sync(FULL, le);
+    gt = __reduce_min_sync(FULL, gt);
+    if ((tid & 31) == 0) {
+      atomicAdd(&s_le, le);
+      atomicMin(&s_gt, gt);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t hi = lo;
+    if (P.k_hi != P.k_lo && P.k_hi >= s_le) hi = s_gt;
+    P.v_min[row] = __uint_as_float(s_min);
+    P.v_lo[row] = __uint_as_float(lo);
+    P.v_hi[row] = __uint_as_float(hi);
+  }
+}
+
+}  // namespace pit

@@ -1,0 +1,176 @@
+"""Fused position-attention: host side above the C ABI.
+
+``position_attention`` is the one functional entry point every ``posatt*`` module of
+``position_induced_transformer_b200.pit`` calls.  It replaces the reference's
+``dist2att`` + ``convolution`` pair (pit.py:46-57, 133-144, 190-200, 247-258) and, for the
+self stage, the ``torch.cat`` of pit.py:44.  Nothing of size N x M is materialised.
+
+Autograd: gradients flow to ``values`` and to the per-head ``scale`` (and from there to
+``lmda`` through ordinary torch ops); meshes are constants, as at every call site of the
+reference.  No gradient flows through the quantile.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+_VARIANTS = ("euclid", "periodic1d", "periodic2d")
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_tensor(name: str, t: torch.Tensor, device: torch.device) -> None:
+    _require(t.is_cuda, f"{name} must be a CUDA tensor (position-attention has no CPU path), got {t.device}")
+    _require(t.device == device, f"{name} is on {t.device}, expected {device}")
+    _require(t.dtype == torch.float32, f"{name} must be float32, got {t.dtype}")
+
+
+class _Stage:
+    """Validated description of one call: the C problem struct plus python-side shape facts."""
+
+    def __init__(self, mesh_out, mesh_in, values, n_head: int, variant: str):
+        _require(variant in _VARIANTS, f"unknown variant {variant!r}")
+        _require(values.dim() == 3, f"values must be (batch, L_in, dim), got {tuple(values.shape)}")
+        device = values.device
+        for name, t in (("values", values), ("mesh_out", mesh_out), ("mesh_in", mesh_in)):
+            _check_tensor(name, t, device)
+        _require(mesh_out.dim() == mesh_in.dim() and mesh_in.dim() in (2, 3),
+                 f"meshes must both be (L, sd) or (batch, L, sd), got {tuple(mesh_out.shape)} / {tuple(mesh_in.shape)}")
+        self.batched = mesh_in.dim() == 3
+        self.B, self.M, self.D = values.shape
+        self.N = mesh_out.shape[-2]
+        self.sd = mesh_in.shape[-1]
+        self.H = int(n_head)
+        _require(mesh_out.shape[-1] == self.sd, "mesh_out / mesh_in disagree on space_dim")
+        _require(self.sd in (1, 2), f"space_dim must be 1 or 2, got {self.sd}")
+        _require(mesh_in.shape[-2] == self.M, f"mesh_in has {mesh_in.shape[-2]} points but values has {self.M}")
+        if self.batched:
+            _require(mesh_in.shape[0] == self.B and mesh_out.shape[0] == self.B, "per-sample meshes must match the batch")
+        self.variant = variant
+        self.device = device
+        self.rows = (self.B if self.batched else 1) * self.N
+        self.problem = _cabi.Problem(_cabi.VARIANT_CODE[variant], self.sd, int(self.batched), self.B, self.H,
+                                     self.N, self.M, self.D)
+
+    def stat_shape(self) -> Tuple[int, ...]:
+        return (self.B, self.N) if self.batched else (self.N,)
+
+    def rowsum_shape(self) -> Tuple[int, ...]:
+        return (self.B, self.H, self.N) if self.batched else (self.H, self.N)
+
+
+def wrap_period(mesh_in: torch.Tensor, variant: str) -> Optional[torch.Tensor]:
+    """Wrap length of the periodic variants as a 1-element device tensor (no host sync).
+
+    periodic1d: |x1 - x0| * M (pit.py:191-192); periodic2d: (max x - min x) / (res - 1) * res with
+    res = int(sqrt(M)) (pit.py:248-250).  Same torch ops, same rounding.
+    """
+    if variant == "periodic1d":
+        return (torch.abs(mesh_in[1, 0] - mesh_in[0, 0]) * mesh_in.shape[0]).reshape(1)
+    if variant == "periodic2d":
+        res = int(mesh_in.shape[0] ** 0.5)
+        return ((torch.max(mesh_in[:, 0]) - torch.min(mesh_in[:, 0])) / (res - 1) * res).reshape(1)
+    return None
+
+
+def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
+    """(v_min, v_lo, v_hi, w, masked): order statistics replacing torch.quantile's row sort."""
+    masked = locality < 1.0
+    k_lo, k_hi, w = _cabi.quantile_ranks(locality, st.M) if masked else (0, 0, 0.0)
+    stats = torch.empty((3,) + st.stat_shape(), dtype=torch.float32, device=st.device)
+    _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
+                                      k_lo, k_hi, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                                      _stream(st.device)), "pit_rowstat")
+    return stats[0], stats[1], stats[2], w, masked
+
+
+def _rowstat_struct(v_min, v_lo, v_hi, w: float, masked: bool) -> _cabi.RowStat:
+    return _cabi.RowStat(v_min.data_ptr(), v_lo.data_ptr() if masked else None, v_hi.data_ptr() if masked else None,
+                         w, int(masked))
+
+
+class _PositionAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, values, scale, mesh_out, mesh_in, n_head, locality, variant, self_concat):
+        values = values.contiguous()
+        mesh_out, mesh_in = mesh_out.contiguous(), mesh_in.contiguous()
+        scale_shape = scale.shape
+        scale = scale.reshape(-1).contiguous()
+        st = _Stage(mesh_out, mesh_in, values, n_head, variant)
+        _check_tensor("scale", scale, st.device)
+        _require(scale.numel() == st.H, f"scale must have n_head={st.H} entries, got {scale.numel()}")
+        if self_concat:
+            _require(st.N == st.M, "self stage needs mesh_out and mesh_in of equal length")
+        with torch.cuda.device(st.device):
+            period = wrap_period(mesh_in, variant)
+            v_min, v_lo, v_hi, w, masked = row_statistics(st, mesh_out, mesh_in, period, float(locality))
+            width = (1 + st.H) * st.D if self_concat else st.H * st.D
+            col_off = st.D if self_concat else 0
+            out = torch.empty((st.B, st.N, width), dtype=torch.float32, device=st.device)
+            rowsum = torch.empty(st.rowsum_shape(), dtype=torch.float32, device=st.device)
+            ws_bytes = int(_cabi.lib.pit_workspace_bytes(C.byref(st.problem)))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=st.device)
+            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
+            _cabi.check(_cabi.lib.pit_posatt_forward(
+                C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
+                scale.data_ptr(), C.byref(rs), out.data_ptr(), width, col_off, int(self_concat), rowsum.data_ptr(),
+                ws.data_ptr(), ws_bytes, _stream(st.device)), "pit_posatt_forward")
+        ctx.save_for_backward(values, scale, mesh_out, mesh_in, period if period is not None else scale.new_empty(0),
+                              v_min, v_lo, v_hi, rowsum)
+        ctx.meta = (n_head, variant, self_concat, w, masked, scale_shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        values, scale, mesh_out, mesh_in, period, v_min, v_lo, v_hi, rowsum = ctx.saved_tensors
+        n_head, variant, self_concat, w, masked, scale_shape = ctx.meta
+        period = period if period.numel() else None
+        st = _Stage(mesh_out, mesh_in, values, n_head, variant)
+        d_out = d_out.contiguous()
+        need_values, need_scale = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_values = d_rows = None
+        with torch.cuda.device(st.device):
+            if need_values:
+                d_values = torch.empty_like(values)
+            if need_scale:
+                d_rows = torch.empty(st.rowsum_shape(), dtype=torch.float32, device=st.device)
+            width = d_out.shape[-1]
+            col_off = st.D if self_concat else 0
+            ws_bytes = int(_cabi.lib.pit_workspace_bytes(C.byref(st.problem)))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=st.device)
+            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
+            _cabi.check(_cabi.lib.pit_posatt_backward(
+                C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
+                scale.data_ptr(), C.byref(rs), rowsum.data_ptr(), d_out.data_ptr(), width, col_off, int(self_concat),
+                _ptr(d_values), _ptr(d_rows), ws.data_ptr(), ws_bytes, _stream(st.device)), "pit_posatt_backward")
+        d_scale = None
+        if need_scale:
+            d_scale = (d_rows.sum(dim=(0, 2)) if st.batched else d_rows.sum(dim=1)).reshape(scale_shape)
+        return d_values, d_scale, None, None, None, None, None, None
+
+
+def position_attention(mesh_out: torch.Tensor, mesh_in: torch.Tensor, values: torch.Tensor, scale: torch.Tensor,
+                       locality: float, variant: str = "euclid", self_concat: bool = False) -> torch.Tensor:
+    """out[b, n, h*D + d] = sum_j softmax_j(-s_h d2(n, j) | quantile mask)[j] * values[b, j, d].
+
+    mesh_out (N, sd) / mesh_in (M, sd) shared by the batch, or (B, N, sd) / (B, M, sd) per sample;
+    values (B, M, D); scale: H positive per-head scales (any shape with H elements).
+    Returns (B, N, H*D), or (B, N, (1+H)*D) = cat(values, out) when ``self_concat``.
+    """
+    return _PositionAttention.apply(values, scale, mesh_out, mesh_in, scale.numel(), float(locality), variant,
+                                    bool(self_concat))
