@@ -27,7 +27,7 @@ from math import pi
 from .posatt import position_attention
 
 __all__ = [
-    "torch", "nn", "gelu", "np", "pi", "kaiming_mlp",
+    "torch", "nn", "gelu", "np", "pi", "kaiming_mlp", "use_host_scale_map",
     "posatt", "posatt_cross", "pit",
     "posatt_fixed", "posatt_cross_fixed", "pit_fixed",
     "posatt_periodic1d", "posatt_cross_periodic1d", "pit_periodic1d",
@@ -38,8 +38,23 @@ __all__ = [
 _SCALE_CONST = 0.25 * pi * (1 - 1e-7)
 
 
+_HOST_SCALE_MAP = False
+
+
+def use_host_scale_map(enabled: bool) -> None:
+    """Parity-testing aid.  The locality mask is decided on values that tie to within one ulp, so the
+    last bit of s_h matters: CUDA's sin/tan and the CPU's differ in that bit for
+    some lmda, which flips mask entries exactly as it does between the reference's own GPU and CPU runs.
+    With the host map enabled the H scalars are evaluated with the CPU's libm (one device->host sync per
+    stage) so that outputs can be compared with a CPU run of the reference to 1e-5."""
+    global _HOST_SCALE_MAP
+    _HOST_SCALE_MAP = bool(enabled)
+
+
 def head_scale(lmda: torch.Tensor) -> torch.Tensor:
     """Per-head positive scale s_h = tan(c * (1 + sin(lmda_h))) (pit.py:48); differentiable torch glue."""
+    if _HOST_SCALE_MAP and lmda.is_cuda:
+        return head_scale(lmda.cpu()).to(lmda.device)
     return torch.tan(_SCALE_CONST * (1.0 + torch.sin(lmda)))
 
 

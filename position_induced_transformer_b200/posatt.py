@@ -88,14 +88,59 @@ def wrap_period(mesh_in: torch.Tensor, variant: str) -> Optional[torch.Tensor]:
     return None
 
 
+class KernelTimer:
+    """Optional per-call CUDA-event timing of the C-ABI launches (used by bench.py for the roofline figures).
+
+    Events are recorded on the stream the kernels are enqueued on; nothing synchronises until ``summary()``.
+    """
+
+    def __init__(self):
+        self.records = []          # (key, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for key, a, b in self.records:
+            tot, n = agg.get(key, (0.0, 0))
+            agg[key] = (tot + a.elapsed_time(b), n + 1)
+        return {k: {"ms_total": tot, "calls": n, "ms_avg": tot / n} for k, (tot, n) in agg.items()}
+
+
+_TIMER: Optional[KernelTimer] = None
+
+
+def set_kernel_timer(timer: Optional[KernelTimer]) -> None:
+    global _TIMER
+    _TIMER = timer
+
+
+class _timed:
+    def __init__(self, tag, st, concat):
+        self.key = (tag, st.variant, int(st.batched), st.B, st.H, st.N, st.M, st.D, st.sd, int(concat))
+        self.dev = st.device
+
+    def __enter__(self):
+        if _TIMER is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream(self.dev))
+
+    def __exit__(self, *exc):
+        if _TIMER is not None and exc[0] is None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(torch.cuda.current_stream(self.dev))
+            _TIMER.records.append((self.key, self.start, end))
+        return False
+
+
 def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
     """(v_min, v_lo, v_hi, w, masked): order statistics replacing torch.quantile's row sort."""
     masked = locality < 1.0
     k_lo, k_hi, w = _cabi.quantile_ranks(locality, st.M) if masked else (0, 0, 0.0)
     stats = torch.empty((3,) + st.stat_shape(), dtype=torch.float32, device=st.device)
-    _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
-                                      k_lo, k_hi, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
-                                      _stream(st.device)), "pit_rowstat")
+    with _timed("rowstat", st, False):
+        _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
+                                          k_lo, k_hi, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                                          _stream(st.device)), "pit_rowstat")
     return stats[0], stats[1], stats[2], w, masked
 
 
@@ -126,10 +171,11 @@ class _PositionAttention(torch.autograd.Function):
             ws_bytes = int(_cabi.lib.pit_workspace_bytes(C.byref(st.problem)))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=st.device)
             rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
-            _cabi.check(_cabi.lib.pit_posatt_forward(
-                C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
-                scale.data_ptr(), C.byref(rs), out.data_ptr(), width, col_off, int(self_concat), rowsum.data_ptr(),
-                ws.data_ptr(), ws_bytes, _stream(st.device)), "pit_posatt_forward")
+            with _timed("fwd", st, self_concat):
+                _cabi.check(_cabi.lib.pit_posatt_forward(
+                    C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
+                    scale.data_ptr(), C.byref(rs), out.data_ptr(), width, col_off, int(self_concat), rowsum.data_ptr(),
+                    ws.data_ptr(), ws_bytes, _stream(st.device)), "pit_posatt_forward")
         ctx.save_for_backward(values, scale, mesh_out, mesh_in, period if period is not None else scale.new_empty(0),
                               v_min, v_lo, v_hi, rowsum)
         ctx.meta = (n_head, variant, self_concat, w, masked, scale_shape)
@@ -154,10 +200,16 @@ class _PositionAttention(torch.autograd.Function):
             ws_bytes = int(_cabi.lib.pit_workspace_bytes(C.byref(st.problem)))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=st.device)
             rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
-            _cabi.check(_cabi.lib.pit_posatt_backward(
-                C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
-                scale.data_ptr(), C.byref(rs), rowsum.data_ptr(), d_out.data_ptr(), width, col_off, int(self_concat),
-                _ptr(d_values), _ptr(d_rows), ws.data_ptr(), ws_bytes, _stream(st.device)), "pit_posatt_backward")
+            # two launches of the same entry point, so that each heavy kernel can be timed on its own
+            for tag, dv, dr in (("bwd_dscale", None, d_rows), ("bwd_dvalues", d_values, None)):
+                if dv is None and dr is None:
+                    continue
+                with _timed(tag, st, self_concat):
+                    _cabi.check(_cabi.lib.pit_posatt_backward(
+                        C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
+                        scale.data_ptr(), C.byref(rs), rowsum.data_ptr(), d_out.data_ptr(), width, col_off,
+                        int(self_concat), _ptr(dv), _ptr(dr), ws.data_ptr(), ws_bytes, _stream(st.device)),
+                        "pit_posatt_backward")
         d_scale = None
         if need_scale:
             d_scale = (d_rows.sum(dim=(0, 2)) if st.batched else d_rows.sum(dim=1)).reshape(scale_shape)

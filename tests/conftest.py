@@ -39,8 +39,18 @@ def variant_of(cls_name: str) -> str:
     return "euclid"
 
 
-def rel_linf(a: torch.Tensor, b: torch.Tensor) -> float:
-    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+def rel_linf(a: torch.Tensor, b: torch.Tensor, floor: float = 1e-30) -> float:
+    """max|a-b| / max(max|b|, floor)."""
+    return float((a - b).abs().max() / b.abs().max().clamp_min(floor))
+
+
+@pytest.fixture
+def host_scale_map():
+    """Evaluate tan/sin of lmda with the CPU's libm, like the CPU run of the reference that made the goldens."""
+    import position_induced_transformer_b200.pit as pit_mod
+    pit_mod.use_host_scale_map(True)
+    yield
+    pit_mod.use_host_scale_map(False)
 
 
 @pytest.fixture(scope="session")

@@ -13,7 +13,7 @@ MODEL_CLASS = {"burgers": "BurgersPiT", "sod": "SodPiT", "darcy43": "DarcyPiT", 
 
 
 @pytest.mark.parametrize("name", golden_names("model_"))
-def test_model_matches_reference(name, cuda_device):
+def test_model_matches_reference(name, cuda_device, host_scale_map):
     from position_induced_transformer_b200 import workloads
     from position_induced_transformer_b200.utils import RelLpNorm
     g = load_golden("model_" + name)

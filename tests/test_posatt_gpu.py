@@ -65,7 +65,7 @@ def test_forward_backward_match_reference(name, cuda_device):
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names("op_")])
-def test_kept_set_equals_reference(name, cuda_device):
+def test_kept_set_equals_reference(name, cuda_device, host_scale_map):
     """Attention exported through the fused kernel (identity values) has the reference's support."""
     import position_induced_transformer_b200.pit as pit_mod
     g = load_golden("op_" + name)
@@ -87,8 +87,8 @@ def test_kept_set_equals_reference(name, cuda_device):
 
 
 @pytest.mark.parametrize("name", golden_names("op_"))
-def test_module_forward_with_device_scale(name, cuda_device):
-    """Whole layer (lmda -> scale on the device) against the reference output."""
+def test_module_forward(name, cuda_device, host_scale_map):
+    """Whole layer (lmda -> scale -> fused op, autograd back to lmda) against the reference output."""
     import position_induced_transformer_b200.pit as pit_mod
     g = load_golden("op_" + name)
     layer = getattr(pit_mod, str(g["cls"]))(int(g["n_head"]), g["values"].shape[-1], float(g["locality"])).to(cuda_device)
@@ -98,10 +98,9 @@ def test_module_forward_with_device_scale(name, cuda_device):
     mo, mi = t(g["mesh_out"], cuda_device), t(g["mesh_in"], cuda_device)
     out = layer(mo, vals) if str(g["kind"]) == "self" else layer(mo, mi, vals)
     out.backward(t(g["upstream"], cuda_device))
-    # sin/tan on the device may differ from the CPU's in the last ulp: allow 4 ulp of scale to show up
-    assert rel_linf(out.detach().cpu(), t(g["out"])) <= 5e-5
-    assert rel_linf(vals.grad.cpu(), t(g["d_values"])) <= 2e-4
-    assert rel_linf(layer.lmda.grad.cpu(), t(g["d_lmda"])) <= 2e-4
+    assert rel_linf(out.detach().cpu(), t(g["out"])) <= FWD_TOL
+    assert rel_linf(vals.grad.cpu(), t(g["d_values"])) <= GRAD_TOL
+    assert rel_linf(layer.lmda.grad.cpu(), t(g["d_lmda"])) <= GRAD_TOL
 
 
 def test_softmax_rows_reproduce_constants(cuda_device):
@@ -175,7 +174,8 @@ def test_ragged_shapes_against_oracle(shape, batched, cuda_device):
         got.backward(up.to(cuda_device))
         assert rel_linf(got.detach().cpu(), want.detach()) <= FWD_TOL
         assert rel_linf(v_gpu.grad.cpu(), v_cpu.grad) <= GRAD_TOL
-        assert rel_linf(s_gpu.grad.cpu().reshape(-1), s_cpu.grad.reshape(-1)) <= GRAD_TOL
+        # a single-column row has an exactly zero scale gradient: compare against the gradient's natural size
+        assert rel_linf(s_gpu.grad.cpu().reshape(-1), s_cpu.grad.reshape(-1), floor=1e-6) <= GRAD_TOL
 
 
 def test_errors_are_loud(cuda_device):
