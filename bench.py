@@ -104,10 +104,8 @@ def algorithmic_bytes(key) -> int:
     values, outs = B * M * D, B * N * H * D
     if tag == "fwd":
         words = values + outs + meshes + (2 * B * N * D if concat else 0)
-    elif tag == "bwd_dscale":      # reads U and dO, writes one scalar per row
-        words = values + outs + meshes
-    elif tag == "bwd_dvalues":     # reads dO (and its concat pass-through), writes dU
-        words = outs + values + meshes + (B * N * D if concat else 0)
+    elif tag == "bwd":             # reads U and dO once (fused scale + value gradients), writes dU
+        words = 2 * values + outs + meshes + (B * N * D if concat else 0)
     else:                          # rowstat: coordinates in, three floats per row out
         words = meshes + 3 * N * (B if batched else 1)
     return 4 * words

@@ -101,12 +101,12 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
 /* Fused backward.  d_out uses the same (ld_out, col_off) addressing as `out`.
  *   d_values [B,M,D]  (may be NULL: not computed).  If accumulate_concat != 0 the first D columns
  *                     of d_out (the concat pass-through, pit.py:44) are added into d_values.
- *   d_scale_rows [(B),H,N]: per-row contribution to dL/ds_h; dL/ds_h = sum over rows (and batch). May be NULL. */
+ *   d_scale [H]       dL/ds_h, summed over rows (and over the batch); overwritten. May be NULL. */
 int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
                         const float* period, const float* values, const float* scale,
                         const pit_rowstat_t* stat, const float* rowsum, const float* d_out,
                         int64_t ld_out, int64_t col_off, int32_t accumulate_concat,
-                        float* d_values, float* d_scale_rows, void* workspace, size_t workspace_bytes,
+                        float* d_values, float* d_scale, void* workspace, size_t workspace_bytes,
                         void* stream);
 
 #ifdef __cplusplus

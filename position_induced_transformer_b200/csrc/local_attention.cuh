@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) posatt_dscale_kernel(con
   }
 }
 
-// d_scale_rows[(b),h,i] = -(A - (m/l) Bq) / l
-__global__ void posatt_dscale_finalize_kernel(const AttnParams P, float* __restrict__ d_scale_rows) {
+// rows[item] = -(A - (m/l) Bq) / l   with item = row * H + h (summed per head by the host-side reduction)
+__global__ void posatt_dscale_finalize_kernel(const AttnParams P, float* __restrict__ rows) {
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rows_total = (P.mesh_batched ? P.B : 1) * P.N;
   if (item >= (int64_t)rows_total * P.H) return;
@@ -324,10 +324,9 @@ __global__ void posatt_dscale_finalize_kernel(const AttnParams P, float* __restr
   const int row = (int)(item / P.H);
   const int bm = P.mesh_batched ? row / P.N : 0;
   const int i = row - bm * P.N;
-  const int64_t stat_idx = ((int64_t)bm * P.H + h) * P.N + i;
-  const float l = P.rowsum[stat_idx];
+  const float l = P.rowsum[((int64_t)bm * P.H + h) * P.N + i];
   const float* term = P.dscale_terms + item * 3;
-  d_scale_rows[stat_idx] = -(term[0] - (term[2] / l) * term[1]) / l;
+  rows[item] = -(term[0] - (term[2] / l) * term[1]) / l;
 }
 
 // ---------------------------------------------------------------------------------------

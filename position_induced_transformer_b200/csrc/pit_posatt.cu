@@ -8,7 +8,9 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <type_traits>
 
+#include "coop_attention.cuh"
 #include "local_attention.cuh"
 #include "rowstat.cuh"
 
@@ -159,6 +161,157 @@ inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 
     default: PIT_DISPATCH_VEC(KERNEL, pit::GEO_PERIODIC2, vec, a, __VA_ARGS__) break;                 \
   }
 
+
+// ---------------------------------------------------------------------------------------------
+// cooperative-CTA kernels (shared meshes, M <= 1024): eligibility, launch shape, dispatch
+// ---------------------------------------------------------------------------------------------
+struct CoopPlan {
+  bool ok;
+  int cpl, l4, lanes4, round_rows, rows_per_cta, grid, n_slots;
+  size_t smem;
+};
+
+int max_smem_optin() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 227 * 1024;
+  }
+  return cached;
+}
+
+CoopPlan plan_coop(const pit_problem_t* p, bool backward, bool with_values) {
+  CoopPlan c{};
+  c.ok = false;
+  if (p->mesh_batched || p->n_in > pit::COOP_MAX_M || p->dim % 4 != 0 || p->n_head > 8) return c;
+  c.lanes4 = p->batch * p->dim / 4;
+  if (c.lanes4 > pit::COOP_MAX_L4 * pit::COOP_THREADS) return c;
+  c.l4 = (c.lanes4 + pit::COOP_THREADS - 1) / pit::COOP_THREADS;
+  if (c.l4 == 3) c.l4 = 4;
+  c.cpl = p->n_in <= 128 ? 4 : (p->n_in <= 256 ? 8 : (p->n_in <= 512 ? 16 : 32));
+  const int budget = max_smem_optin();
+  // slots for the value gradient: enough for the columns a few neighbouring rows touch
+  c.n_slots = 0;
+  if (with_values) {
+    const int per_slot = c.lanes4 * 16;
+    c.n_slots = 48 * 1024 / per_slot;
+    if (c.n_slots > 64) c.n_slots = 64;
+    if (c.n_slots > p->n_in) c.n_slots = p->n_in;
+    if (c.n_slots < 4) return c;
+  }
+  c.round_rows = (backward || p->n_out < 148 * 8) ? 4 : 8;
+  c.smem = pit::coop_smem_bytes(c.round_rows, p->n_head, p->n_in, c.lanes4, backward, c.n_slots);
+  if (c.smem > (size_t)budget / 2) {
+    c.round_rows = 4;
+    c.smem = pit::coop_smem_bytes(c.round_rows, p->n_head, p->n_in, c.lanes4, backward, c.n_slots);
+  }
+  if (c.smem > (size_t)budget - 1024) return c;
+  int per_sm = (int)((size_t)budget / (c.smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const int target = sm_count() * per_sm;
+  int rows = (p->n_out + target - 1) / target;
+  rows = (rows + c.round_rows - 1) / c.round_rows * c.round_rows;
+  c.rows_per_cta = rows;
+  c.grid = (p->n_out + rows - 1) / rows;
+  c.ok = true;
+  return c;
+}
+
+pit::CoopParams coop_params(const pit_problem_t* p, const CoopPlan& c, const float* mesh_out, const float* mesh_in,
+                            const float* period, const float* values, const float* scale, const pit_rowstat_t* st) {
+  pit::CoopParams P{};
+  P.mesh_out = mesh_out;
+  P.mesh_in = mesh_in;
+  P.period = p->variant == PIT_EUCLID ? nullptr : period;
+  P.values = values;
+  P.scale = scale;
+  P.v_min = st->v_min;
+  P.v_lo = st->v_lo;
+  P.v_hi = st->v_hi;
+  P.weight = st->weight;
+  P.masked = st->masked;
+  P.B = p->batch;
+  P.H = p->n_head;
+  P.N = p->n_out;
+  P.M = p->n_in;
+  P.D = p->dim;
+  P.sd = p->space_dim;
+  P.lanes4 = c.lanes4;
+  P.round_rows = c.round_rows;
+  P.rows_per_cta = c.rows_per_cta;
+  P.n_slots = c.n_slots;
+  return P;
+}
+
+template <typename K>
+cudaError_t coop_launch(K kernel, const CoopPlan& c, const pit::CoopParams& P, cudaStream_t st) {
+  if (c.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) return e;
+  }
+  kernel<<<c.grid, pit::COOP_THREADS, c.smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <int V>
+using Int = std::integral_constant<int, V>;
+
+// Calls f(Int<GEO>, Int<CPL>, Int<L4>) for the runtime (geo, cpl, l4).
+template <typename G, typename C, typename F>
+cudaError_t with_l4(G g, C c, int l4, F&& f) {
+  if (l4 == 1) return f(g, c, Int<1>{});
+  if (l4 == 2) return f(g, c, Int<2>{});
+  return f(g, c, Int<4>{});
+}
+template <typename G, typename F>
+cudaError_t with_cpl(G g, int cpl, int l4, F&& f) {
+  if (cpl == 4) return with_l4(g, Int<4>{}, l4, f);
+  if (cpl == 8) return with_l4(g, Int<8>{}, l4, f);
+  if (cpl == 16) return with_l4(g, Int<16>{}, l4, f);
+  return with_l4(g, Int<32>{}, l4, f);
+}
+template <typename F>
+cudaError_t with_geo(int geo, int cpl, int l4, F&& f) {
+  if (geo == pit::GEO_EUCLID1) return with_cpl(Int<pit::GEO_EUCLID1>{}, cpl, l4, f);
+  if (geo == pit::GEO_EUCLID2) return with_cpl(Int<pit::GEO_EUCLID2>{}, cpl, l4, f);
+  if (geo == pit::GEO_PERIODIC1) return with_cpl(Int<pit::GEO_PERIODIC1>{}, cpl, l4, f);
+  return with_cpl(Int<pit::GEO_PERIODIC2>{}, cpl, l4, f);
+}
+
+cudaError_t coop_forward(int geo, const CoopPlan& plan, const pit::CoopParams& P, cudaStream_t st) {
+  return with_geo(geo, plan.cpl, plan.l4, [&](auto g, auto c, auto l) {
+    return coop_launch(pit::coop_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(l)::value>, plan, P, st);
+  });
+}
+cudaError_t coop_backward(int geo, const CoopPlan& plan, const pit::CoopParams& P, bool with_values, cudaStream_t st) {
+  return with_geo(geo, plan.cpl, plan.l4, [&](auto g, auto c, auto l) {
+    constexpr int G = decltype(g)::value, C = decltype(c)::value, L = decltype(l)::value;
+    return with_values ? coop_launch(pit::coop_bwd_kernel<G, C, L, true>, plan, P, st)
+                       : coop_launch(pit::coop_bwd_kernel<G, C, L, false>, plan, P, st);
+  });
+}
+
+// Sum of the per-row scale-gradient terms of one head (generic path): d_scale[h] = sum_rows rows[row*H + h].
+__global__ void reduce_scale_rows_kernel(const float* __restrict__ rows, int64_t n_rows, int H, float* __restrict__ d_scale) {
+  __shared__ float red[32];
+  const int h = blockIdx.x;
+  float acc = 0.f;
+  for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) acc += rows[r * H + h];
+  acc = pit::warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    d_scale[h] = t;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -184,7 +337,7 @@ size_t pit_workspace_bytes(const pit_problem_t* p) {
   const int64_t rows_total = (int64_t)(p->mesh_batched ? p->batch : 1) * p->n_out;
   const Shape f = make_shape(p, rows_total * p->n_head, p->n_in, true);
   size_t fwd = f.n_split > 1 ? (size_t)f.items * f.width * sizeof(float) : 0;
-  size_t bwd = (size_t)rows_total * p->n_head * 3 * sizeof(float);
+  size_t bwd = (size_t)rows_total * p->n_head * 4 * sizeof(float);
   size_t need = fwd > bwd ? fwd : bwd;
   return need + 256;
 }
@@ -246,6 +399,21 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
   if (s.vec == 4 && (!aligned16(values) || !aligned16(out) || (ld_out % 4) || (col_off % 4))) {
     return fail(PIT_ERR_ARG, "values/out must be 16-byte aligned with ld_out, col_off multiples of 4 when D %% 4 == 0");
   }
+  if (copy_values) {  // first D columns of the concat output (pit.py:44)
+    PIT_CUDA(cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(float), values, (size_t)p->dim * sizeof(float),
+                               (size_t)p->dim * sizeof(float), (size_t)p->batch * p->n_in, cudaMemcpyDeviceToDevice, st));
+  }
+  const CoopPlan plan = plan_coop(p, false, false);
+  if (plan.ok) {
+    pit::CoopParams C = coop_params(p, plan, mesh_out, mesh_in, period, values, scale, stat);
+    C.out = out;
+    C.ld_out = ld_out;
+    C.col_off = col_off;
+    C.rowsum = rowsum;
+    PIT_CUDA(coop_forward(geo_of(p), plan, C, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PIT_OK;
+  }
   pit::AttnParams P = base_params(p, mesh_out, mesh_in, period, values, scale, stat);
   P.out = out;
   P.ld_out = ld_out;
@@ -258,10 +426,6 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     P.partial = static_cast<float*>(workspace);
     PIT_CUDA(cudaMemsetAsync(P.partial, 0, need, st));
     PIT_CUDA(cudaMemsetAsync(rowsum, 0, (size_t)s.items * sizeof(float), st));
-  }
-  if (copy_values) {  // first D columns of the concat output (pit.py:44)
-    PIT_CUDA(cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(float), values, (size_t)p->dim * sizeof(float),
-                               (size_t)p->dim * sizeof(float), (size_t)p->batch * p->n_in, cudaMemcpyDeviceToDevice, st));
   }
   const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
   const dim3 block(pit::WARPS_PER_BLOCK * 32);
@@ -278,7 +442,7 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
 int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
                         const float* values, const float* scale, const pit_rowstat_t* stat, const float* rowsum,
                         const float* d_out, int64_t ld_out, int64_t col_off, int32_t accumulate_concat, float* d_values,
-                        float* d_scale_rows, void* workspace, size_t workspace_bytes, void* stream) {
+                        float* d_scale, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (!mesh_out || !mesh_in || !values || !scale || !rowsum || !d_out) return fail(PIT_ERR_ARG, "null pointer");
   if (int rc = check_stat(p, stat, period)) return rc;
@@ -292,6 +456,31 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   const bool vec4 = p->dim % 4 == 0;
   if (vec4 && (!aligned16(values) || !aligned16(d_out) || (d_values && !aligned16(d_values)) || (ld_out % 4) || (col_off % 4)))
     return fail(PIT_ERR_ARG, "values/d_out/d_values must be 16-byte aligned with ld_out, col_off multiples of 4 when D %% 4 == 0");
+
+  // Cooperative path (shared meshes, M <= 1024): one pass over d_out gives the scale gradient and, for a
+  // masked cross stage, the value gradient too.  A dense self stage keeps the value gradient on the
+  // column-owner kernel below (every column is touched by every row, slots would not help).
+  bool values_done = d_values == nullptr, scale_done = d_scale == nullptr;
+  {
+    const bool fuse_values = d_values && stat->masked && !accumulate_concat;
+    const CoopPlan plan = plan_coop(p, true, fuse_values);
+    if (plan.ok && (d_scale || fuse_values)) {
+      pit::CoopParams C = coop_params(p, plan, mesh_out, mesh_in, period, values, scale, stat);
+      C.rowsum = const_cast<float*>(rowsum);
+      C.d_out = d_out;
+      C.ld_out = ld_out;
+      C.col_off = col_off;
+      C.d_values = fuse_values ? d_values : nullptr;
+      C.d_scale = d_scale;
+      if (d_scale) PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
+      if (fuse_values) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
+      PIT_CUDA(coop_backward(geo, plan, C, fuse_values, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      scale_done = true;
+      if (fuse_values) values_done = true;
+    }
+  }
+
   pit::AttnParams P = base_params(p, mesh_out, mesh_in, period, values, scale, stat);
   P.rowsum = const_cast<float*>(rowsum);
   P.d_out = d_out;
@@ -301,20 +490,23 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   P.add_concat = accumulate_concat;
   const dim3 block(pit::WARPS_PER_BLOCK * 32);
 
-  if (d_scale_rows) {
+  if (!scale_done) {
     Shape s = make_shape(p, rows_total * p->n_head, p->n_in, true);
-    const size_t need = (size_t)s.items * 3 * sizeof(float);
+    const size_t need = (size_t)s.items * 4 * sizeof(float);
     if (!workspace || workspace_bytes < need) return fail(PIT_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
     P.dscale_terms = static_cast<float*>(workspace);
+    float* rows = P.dscale_terms + (size_t)s.items * 3;
     P.split_len = s.split_len;
-    PIT_CUDA(cudaMemsetAsync(P.dscale_terms, 0, need, st));
+    PIT_CUDA(cudaMemsetAsync(P.dscale_terms, 0, (size_t)s.items * 3 * sizeof(float), st));
     const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
     PIT_DISPATCH(pit::posatt_dscale_kernel, geo, s.vec, s.a, <<<grid, block, 0, st>>>(P));
     PIT_LAUNCHED();
-    pit::posatt_dscale_finalize_kernel<<<(unsigned)((s.items + 255) / 256), 256, 0, st>>>(P, d_scale_rows);
+    pit::posatt_dscale_finalize_kernel<<<(unsigned)((s.items + 255) / 256), 256, 0, st>>>(P, rows);
+    PIT_LAUNCHED();
+    reduce_scale_rows_kernel<<<p->n_head, 512, 0, st>>>(rows, rows_total, p->n_head, d_scale);
     PIT_LAUNCHED();
   }
-  if (d_values) {
+  if (!values_done) {
     Shape s = make_shape(p, cols_total, p->n_out * p->n_head, true);
     // the sweep runs over rows i for every head, so the split is expressed in rows
     if (s.n_split > 1) {

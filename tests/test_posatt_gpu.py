@@ -188,3 +188,24 @@ def test_errors_are_loud(cuda_device):
            torch.ones(1, device=cuda_device), 0.5)                                                           # space_dim 3
     with pytest.raises(RuntimeError):
         pa(mesh, mesh, torch.rand(1, 8, 4, device=cuda_device).double(), torch.ones(1, device=cuda_device), 0.5)
+
+
+def test_rowstat_cache_hits_and_invalidates(cuda_device):
+    from position_induced_transformer_b200 import posatt
+    pa = _pa()
+    gen = torch.Generator().manual_seed(21)
+    mo = torch.rand(50, 2, generator=gen).to(cuda_device)
+    mi = torch.rand(300, 2, generator=gen).to(cuda_device)
+    vals = torch.randn(2, 300, 4, generator=gen).to(cuda_device)
+    scale = torch.tensor([2.0], device=cuda_device)
+    posatt.rowstat_cache.clear()
+    h0, m0 = posatt.rowstat_cache.hits, posatt.rowstat_cache.misses
+    a = pa(mo, mi, vals, scale, 0.1)
+    b = pa(mo.reshape(-1, 2), mi, vals, scale, 0.1)          # a fresh view of the same storage hits
+    assert posatt.rowstat_cache.misses == m0 + 1 and posatt.rowstat_cache.hits == h0 + 1
+    assert torch.equal(a, b)
+    mi[0, 0] += 0.25                                          # in-place write bumps the version: miss, new statistics
+    c = pa(mo, mi, vals, scale, 0.1)
+    assert posatt.rowstat_cache.misses == m0 + 2
+    want = po.dense_contract(po.dense_attention(mo.cpu(), mi.cpu(), scale.cpu().reshape(-1, 1, 1), 0.1), vals.cpu())
+    assert rel_linf(c.cpu(), want) <= FWD_TOL
