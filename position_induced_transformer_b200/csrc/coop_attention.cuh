@@ -29,7 +29,9 @@ namespace pit {
 constexpr int COOP_THREADS = 128;
 constexpr int COOP_WARPS = COOP_THREADS / 32;
 constexpr int COOP_MAX_M = 1024;
-constexpr int COOP_MAX_L4 = 4;  // float4 lanes per thread: B*D <= 4 * 128 * 4 = 2048
+constexpr int COOP_MAX_L4 = 4;      // float4 lanes per thread: B*D <= 4 * 128 * 4 = 2048
+constexpr int COOP_GATHER = 8;      // independent value-row gathers in flight per thread (forward)
+constexpr int COOP_GATHER_BWD = 8;  // same, backward
 
 struct CoopParams {
   const float* mesh_out;  // [N,sd]
@@ -218,18 +220,28 @@ __global__ void __launch_bounds__(COOP_THREADS) coop_fwd_kernel(const CoopParams
         float4 acc[L4];
 #pragma unroll
         for (int k = 0; k < L4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int e = 0; e < n; ++e) {
-          const int64_t joff = (int64_t)sj[e] * P.D;
-          const float p = sp[e];
+        for (int e0 = 0; e0 < n; e0 += COOP_GATHER) {
+          // issue a whole batch of independent 128-bit gathers before the first FMA consumes one
+          float4 u[COOP_GATHER][L4];
+          float pw[COOP_GATHER];
 #pragma unroll
-          for (int k = 0; k < L4; ++k) {
-            if (ok[k]) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(P.values + val_off[k] + joff));
-              acc[k].x = fmaf(p, u.x, acc[k].x);
-              acc[k].y = fmaf(p, u.y, acc[k].y);
-              acc[k].z = fmaf(p, u.z, acc[k].z);
-              acc[k].w = fmaf(p, u.w, acc[k].w);
+          for (int t = 0; t < COOP_GATHER; ++t) {
+            const bool live = e0 + t < n;
+            const int64_t joff = live ? (int64_t)sj[e0 + t] * P.D : 0;
+            pw[t] = live ? sp[e0 + t] : 0.f;
+#pragma unroll
+            for (int k = 0; k < L4; ++k)
+              u[t][k] = (live && ok[k]) ? __ldg(reinterpret_cast<const float4*>(P.values + val_off[k] + joff))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int t = 0; t < COOP_GATHER; ++t) {
+#pragma unroll
+            for (int k = 0; k < L4; ++k) {
+              acc[k].x = fmaf(pw[t], u[t][k].x, acc[k].x);
+              acc[k].y = fmaf(pw[t], u[t][k].y, acc[k].y);
+              acc[k].z = fmaf(pw[t], u[t][k].z, acc[k].z);
+              acc[k].w = fmaf(pw[t], u[t][k].w, acc[k].w);
             }
           }
         }
@@ -316,6 +328,22 @@ __global__ void __launch_bounds__(COOP_THREADS) coop_bwd_kernel(const CoopParams
   const int row_end = min(P.N, row_begin + P.rows_per_cta);
   for (int r0 = row_begin; r0 < row_end; r0 += P.round_rows) {
     const int in_round = min(P.round_rows, row_end - r0);
+    // Pull the next round's d_out rows into L2 while this round is being processed (each thread its own lane).
+    {
+      const int nr0 = r0 + P.round_rows;
+      const int n_next = min(P.round_rows, row_end - nr0);
+      for (int w = 0; w < n_next; ++w) {
+        for (int h = 0; h < P.H; ++h) {
+#pragma unroll
+          for (int k = 0; k < L4; ++k) {
+            if (ok[k]) {
+              const float* q = P.d_out + g_off[k] + (int64_t)(nr0 + w) * P.ld_out + (int64_t)h * P.D;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+          }
+        }
+      }
+    }
     // ---- phase 1: normalised weights (l is known from the forward pass) ----
     for (int w = warp; w < in_round; w += COOP_WARPS) {
       const int r = r0 + w;
@@ -396,39 +424,59 @@ __global__ void __launch_bounds__(COOP_THREADS) coop_bwd_kernel(const CoopParams
           acc_o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           acc_w[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-#pragma unroll 2
-        for (int e = 0; e < n; ++e) {
-          const int j = sj[e];
-          const int64_t joff = (int64_t)j * P.D;
-          const float p = sp[e], pd = spd[e];
-          int sidx = -1;
-          if (WITH_VALUES) sidx = S.map[j];
+        for (int e0 = 0; e0 < n; e0 += COOP_GATHER_BWD) {
+          float4 u[COOP_GATHER_BWD][L4];
+          float pw[COOP_GATHER_BWD], pdw[COOP_GATHER_BWD];
+          int jj[COOP_GATHER_BWD];
 #pragma unroll
-          for (int k = 0; k < L4; ++k) {
-            if (!ok[k]) continue;
+          for (int t = 0; t < COOP_GATHER_BWD; ++t) {
+            const bool live = e0 + t < n;
+            jj[t] = live ? (int)sj[e0 + t] : -1;
+            pw[t] = live ? sp[e0 + t] : 0.f;
+            pdw[t] = live ? spd[e0 + t] : 0.f;
             if (want_scale) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(P.values + val_off[k] + joff));
-              acc_o[k].x = fmaf(p, u.x, acc_o[k].x);
-              acc_o[k].y = fmaf(p, u.y, acc_o[k].y);
-              acc_o[k].z = fmaf(p, u.z, acc_o[k].z);
-              acc_o[k].w = fmaf(p, u.w, acc_o[k].w);
-              acc_w[k].x = fmaf(pd, u.x, acc_w[k].x);
-              acc_w[k].y = fmaf(pd, u.y, acc_w[k].y);
-              acc_w[k].z = fmaf(pd, u.z, acc_w[k].z);
-              acc_w[k].w = fmaf(pd, u.w, acc_w[k].w);
+#pragma unroll
+              for (int k = 0; k < L4; ++k)
+                u[t][k] = (live && ok[k]) ? __ldg(reinterpret_cast<const float4*>(P.values + val_off[k] + (int64_t)jj[t] * P.D))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (WITH_VALUES) {
-              const float4 add = make_float4(p * g[k].x, p * g[k].y, p * g[k].z, p * g[k].w);
-              if (sidx >= 0) {
-                float4* cell = S.slot_acc + (size_t)sidx * P.lanes4 + tid + k * COOP_THREADS;
-                float4 cur = *cell;
-                cur.x += add.x;
-                cur.y += add.y;
-                cur.z += add.z;
-                cur.w += add.w;
-                *cell = cur;
-              } else {
-                atomicAdd(reinterpret_cast<float4*>(P.d_values + val_off[k] + joff), add);
+          }
+          if (want_scale) {
+#pragma unroll
+            for (int t = 0; t < COOP_GATHER_BWD; ++t) {
+#pragma unroll
+              for (int k = 0; k < L4; ++k) {
+                acc_o[k].x = fmaf(pw[t], u[t][k].x, acc_o[k].x);
+                acc_o[k].y = fmaf(pw[t], u[t][k].y, acc_o[k].y);
+                acc_o[k].z = fmaf(pw[t], u[t][k].z, acc_o[k].z);
+                acc_o[k].w = fmaf(pw[t], u[t][k].w, acc_o[k].w);
+                acc_w[k].x = fmaf(pdw[t], u[t][k].x, acc_w[k].x);
+                acc_w[k].y = fmaf(pdw[t], u[t][k].y, acc_w[k].y);
+                acc_w[k].z = fmaf(pdw[t], u[t][k].z, acc_w[k].z);
+                acc_w[k].w = fmaf(pdw[t], u[t][k].w, acc_w[k].w);
+              }
+            }
+          }
+          if (WITH_VALUES) {
+#pragma unroll
+            for (int t = 0; t < COOP_GATHER_BWD; ++t) {
+              if (jj[t] < 0) continue;
+              const int sidx = S.map[jj[t]];
+#pragma unroll
+              for (int k = 0; k < L4; ++k) {
+                if (!ok[k]) continue;
+                const float4 add = make_float4(pw[t] * g[k].x, pw[t] * g[k].y, pw[t] * g[k].z, pw[t] * g[k].w);
+                if (sidx >= 0) {
+                  float4* cell = S.slot_acc + (size_t)sidx * P.lanes4 + tid + k * COOP_THREADS;
+                  float4 cur = *cell;
+                  cur.x += add.x;
+                  cur.y += add.y;
+                  cur.z += add.z;
+                  cur.w += add.w;
+                  *cell = cur;
+                } else {
+                  atomicAdd(reinterpret_cast<float4*>(P.d_values + val_off[k] + (int64_t)jj[t] * P.D), add);
+                }
               }
             }
           }

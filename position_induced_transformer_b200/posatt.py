@@ -132,13 +132,15 @@ class _timed:
         return False
 
 
-class _RowstatCache:
-    """Order statistics of shared meshes, reused across steps.
+class _MeshCache:
+    """Per-mesh-pair constants of shared meshes, reused across steps.
 
-    v_min / v_lo / v_hi depend on the two meshes and on the locality only -- not on lmda -- and the
-    scripts pass the same mesh tensors at every step (train_darcy.py:88-96, 128), while the reference
-    re-sorts every row each time (pit.py:136).  An entry is keyed by the storage address, offset, shape,
-    strides and autograd version of both meshes and keeps a strong reference to them, so the address
+    For a pair of shared meshes the contiguous copies, the wrap period and the order statistics
+    v_min / v_lo / v_hi depend on the meshes and the locality only -- not on lmda -- and the scripts
+    pass the same mesh tensors at every step (train_darcy.py:88-96, 128; note that they are column-major
+    views of a transposed numpy array, so even `.contiguous()` is a copy), while the reference re-sorts
+    every row each time (pit.py:136).  An entry is keyed by the storage address, offset, shape, strides
+    and autograd version of both incoming tensors and keeps a strong reference to them, so the address
     cannot be recycled while the entry lives and any in-place write (which bumps the version) misses.
     Per-sample meshes (posatt / posatt_cross) change every batch and are never cached.
     """
@@ -153,8 +155,8 @@ class _RowstatCache:
     def _sig(t: torch.Tensor):
         return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version, t.device.index)
 
-    def key(self, mesh_out, mesh_in, variant, k_lo, k_hi):
-        return (self._sig(mesh_out), self._sig(mesh_in), variant, k_lo, k_hi)
+    def key(self, mesh_out, mesh_in, variant, locality):
+        return (self._sig(mesh_out), self._sig(mesh_in), variant, float(locality))
 
     def get(self, key):
         hit = self.entries.get(key)
@@ -164,34 +166,48 @@ class _RowstatCache:
         self.hits += 1
         return hit[0]
 
-    def put(self, key, stats, keep_alive):
+    def put(self, key, value, keep_alive):
         if len(self.entries) >= self.capacity:
             self.entries.pop(next(iter(self.entries)))
-        self.entries[key] = (stats, keep_alive)
+        self.entries[key] = (value, keep_alive)
 
     def clear(self):
         self.entries.clear()
 
 
-rowstat_cache = _RowstatCache()
+mesh_cache = _MeshCache()
+rowstat_cache = mesh_cache          # historical name
 
 
 def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
-    """(v_min, v_lo, v_hi, w, masked): order statistics replacing torch.quantile's row sort."""
+    """(v_min, v_lo, v_hi, w, masked): order statistics replacing torch.quantile's row sort (uncached)."""
     masked = locality < 1.0
     k_lo, k_hi, w = _cabi.quantile_ranks(locality, st.M) if masked else (0, 0, 0.0)
-    cacheable = rowstat_cache.enabled and not st.batched and not torch.cuda.is_current_stream_capturing()
-    key = rowstat_cache.key(mesh_out, mesh_in, st.variant, k_lo, k_hi) if cacheable else None
-    stats = rowstat_cache.get(key) if cacheable else None
-    if stats is None:
-        stats = torch.empty((3,) + st.stat_shape(), dtype=torch.float32, device=st.device)
-        with _timed("rowstat", st, False):
-            _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
-                                              k_lo, k_hi, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
-                                              _stream(st.device)), "pit_rowstat")
-        if cacheable:
-            rowstat_cache.put(key, stats, (mesh_out, mesh_in))
+    stats = torch.empty((3,) + st.stat_shape(), dtype=torch.float32, device=st.device)
+    with _timed("rowstat", st, False):
+        _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
+                                          k_lo, k_hi, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                                          _stream(st.device)), "pit_rowstat")
     return stats[0], stats[1], stats[2], w, masked
+
+
+def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, locality: float):
+    """Contiguous meshes, the validated stage, the wrap period and the row statistics -- cached for shared meshes."""
+    batched = mesh_in.dim() == 3
+    cacheable = mesh_cache.enabled and not batched and mesh_in.is_cuda and not torch.cuda.is_current_stream_capturing()
+    key = mesh_cache.key(mesh_out, mesh_in, variant, locality) if cacheable else None
+    hit = mesh_cache.get(key) if cacheable else None
+    if hit is not None:
+        mo, mi, period, stats = hit
+        return mo, mi, _Stage(mo, mi, values, n_head, variant), period, stats
+    mo, mi = mesh_out.contiguous(), mesh_in.contiguous()
+    st = _Stage(mo, mi, values, n_head, variant)
+    with torch.cuda.device(st.device):
+        period = wrap_period(mi, variant)
+        stats = row_statistics(st, mo, mi, period, float(locality))
+    if cacheable:
+        mesh_cache.put(key, (mo, mi, period, stats), (mesh_out, mesh_in))
+    return mo, mi, st, period, stats
 
 
 def _rowstat_struct(v_min, v_lo, v_hi, w: float, masked: bool) -> _cabi.RowStat:
@@ -203,17 +219,16 @@ class _PositionAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, values, scale, mesh_out, mesh_in, n_head, locality, variant, self_concat):
         values = values.contiguous()
-        mesh_out, mesh_in = mesh_out.contiguous(), mesh_in.contiguous()
+        _require(values.is_cuda, f"values must be a CUDA tensor (position-attention has no CPU path), got {values.device}")
         scale_shape = scale.shape
         scale = scale.reshape(-1).contiguous()
-        st = _Stage(mesh_out, mesh_in, values, n_head, variant)
+        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked) = prepare_meshes(
+            mesh_out, mesh_in, values, n_head, variant, float(locality))
         _check_tensor("scale", scale, st.device)
         _require(scale.numel() == st.H, f"scale must have n_head={st.H} entries, got {scale.numel()}")
         if self_concat:
             _require(st.N == st.M, "self stage needs mesh_out and mesh_in of equal length")
         with torch.cuda.device(st.device):
-            period = wrap_period(mesh_in, variant)
-            v_min, v_lo, v_hi, w, masked = row_statistics(st, mesh_out, mesh_in, period, float(locality))
             width = (1 + st.H) * st.D if self_concat else st.H * st.D
             col_off = st.D if self_concat else 0
             out = torch.empty((st.B, st.N, width), dtype=torch.float32, device=st.device)
