@@ -10,7 +10,7 @@
 #include <atomic>
 #include <type_traits>
 
-#include "coop_attention.cuh"
+#include "tall_attention.cuh"
 #include "local_attention.cuh"
 #include "rowstat.cuh"
 
@@ -163,11 +163,11 @@ inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 
 
 
 // ---------------------------------------------------------------------------------------------
-// cooperative-CTA kernels (shared meshes, M <= 1024): eligibility, launch shape, dispatch
+// "tall" kernels (shared meshes, M <= 1024, H <= 2): eligibility, launch shape, dispatch
 // ---------------------------------------------------------------------------------------------
-struct CoopPlan {
+struct TallPlan {
   bool ok;
-  int cpl, l4, lanes4, round_rows, rows_per_cta, grid, n_slots;
+  int cpl, l4, lanes4, chunks, rows_per_unit, grid, n_slots;
   size_t smem;
 };
 
@@ -184,17 +184,41 @@ int max_smem_optin() {
   return cached;
 }
 
-CoopPlan plan_coop(const pit_problem_t* p, bool backward, bool with_values) {
-  CoopPlan c{};
-  c.ok = false;
-  if (p->mesh_batched || p->n_in > pit::COOP_MAX_M || p->dim % 4 != 0 || p->n_head > 8) return c;
+bool tall_eligible(const pit_problem_t* p) {
+  return !p->mesh_batched && p->n_in <= pit::TALL_MAX_M && p->dim % 4 == 0 && p->n_head <= pit::TALL_MAX_H;
+}
+
+int cpl_of(int m) { return m <= 128 ? 4 : (m <= 256 ? 8 : (m <= 512 ? 16 : 32)); }
+
+// forward: one warp per row, 32*l4 float4 lanes per warp pass, `chunks` passes over blockIdx.y
+TallPlan plan_tall_fwd(const pit_problem_t* p) {
+  TallPlan c{};
+  if (!tall_eligible(p)) return c;
   c.lanes4 = p->batch * p->dim / 4;
-  if (c.lanes4 > pit::COOP_MAX_L4 * pit::COOP_THREADS) return c;
-  c.l4 = (c.lanes4 + pit::COOP_THREADS - 1) / pit::COOP_THREADS;
+  c.l4 = c.lanes4 >= 128 ? 4 : (c.lanes4 >= 64 ? 2 : 1);
+  c.chunks = (c.lanes4 + 32 * c.l4 - 1) / (32 * c.l4);
+  c.cpl = cpl_of(p->n_in);
+  c.smem = (size_t)pit::TALL_WARPS * c.cpl * 32 * 16;
+  const int64_t warps_wanted = (int64_t)sm_count() * 24;
+  int64_t rows = (p->n_out + warps_wanted - 1) / warps_wanted;
+  if (rows < 1) rows = 1;
+  c.rows_per_unit = (int)rows;
+  const int64_t warps = (p->n_out + rows - 1) / rows;
+  c.grid = (int)((warps + pit::TALL_WARPS - 1) / pit::TALL_WARPS);
+  c.ok = true;
+  return c;
+}
+
+// backward: CTA-cooperative, thread owns l4 float4 lanes, lanes4 <= 4 * 128
+TallPlan plan_tall_bwd(const pit_problem_t* p, bool with_values) {
+  TallPlan c{};
+  if (!tall_eligible(p)) return c;
+  c.lanes4 = p->batch * p->dim / 4;
+  if (c.lanes4 > 4 * pit::TALL_THREADS) return c;
+  c.l4 = (c.lanes4 + pit::TALL_THREADS - 1) / pit::TALL_THREADS;
   if (c.l4 == 3) c.l4 = 4;
-  c.cpl = p->n_in <= 128 ? 4 : (p->n_in <= 256 ? 8 : (p->n_in <= 512 ? 16 : 32));
+  c.cpl = cpl_of(p->n_in);
   const int budget = max_smem_optin();
-  // slots for the value gradient: enough for the columns a few neighbouring rows touch
   c.n_slots = 0;
   if (with_values) {
     const int per_slot = c.lanes4 * 16;
@@ -203,28 +227,24 @@ CoopPlan plan_coop(const pit_problem_t* p, bool backward, bool with_values) {
     if (c.n_slots > p->n_in) c.n_slots = p->n_in;
     if (c.n_slots < 4) return c;
   }
-  c.round_rows = (backward || p->n_out < 148 * 8) ? 4 : 8;
-  c.smem = pit::coop_smem_bytes(c.round_rows, p->n_head, p->n_in, c.lanes4, backward, c.n_slots);
-  if (c.smem > (size_t)budget / 2) {
-    c.round_rows = 4;
-    c.smem = pit::coop_smem_bytes(c.round_rows, p->n_head, p->n_in, c.lanes4, backward, c.n_slots);
-  }
+  c.smem = pit::tall_bwd_smem_bytes(c.cpl, p->n_in, c.lanes4, c.n_slots);
   if (c.smem > (size_t)budget - 1024) return c;
   int per_sm = (int)((size_t)budget / (c.smem + 1024));
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
   const int target = sm_count() * per_sm;
   int rows = (p->n_out + target - 1) / target;
-  rows = (rows + c.round_rows - 1) / c.round_rows * c.round_rows;
-  c.rows_per_cta = rows;
+  rows = (rows + pit::TALL_WARPS - 1) / pit::TALL_WARPS * pit::TALL_WARPS;
+  c.rows_per_unit = rows;
   c.grid = (p->n_out + rows - 1) / rows;
+  c.chunks = 1;
   c.ok = true;
   return c;
 }
 
-pit::CoopParams coop_params(const pit_problem_t* p, const CoopPlan& c, const float* mesh_out, const float* mesh_in,
+pit::TallParams tall_params(const pit_problem_t* p, const TallPlan& c, const float* mesh_out, const float* mesh_in,
                             const float* period, const float* values, const float* scale, const pit_rowstat_t* st) {
-  pit::CoopParams P{};
+  pit::TallParams P{};
   P.mesh_out = mesh_out;
   P.mesh_in = mesh_in;
   P.period = p->variant == PIT_EUCLID ? nullptr : period;
@@ -242,57 +262,61 @@ pit::CoopParams coop_params(const pit_problem_t* p, const CoopPlan& c, const flo
   P.D = p->dim;
   P.sd = p->space_dim;
   P.lanes4 = c.lanes4;
-  P.round_rows = c.round_rows;
-  P.rows_per_cta = c.rows_per_cta;
+  P.rows_per_unit = c.rows_per_unit;
   P.n_slots = c.n_slots;
   return P;
 }
 
 template <typename K>
-cudaError_t coop_launch(K kernel, const CoopPlan& c, const pit::CoopParams& P, cudaStream_t st) {
+cudaError_t tall_launch(K kernel, const TallPlan& c, const pit::TallParams& P, cudaStream_t st) {
   if (c.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return e;
   }
-  kernel<<<c.grid, pit::COOP_THREADS, c.smem, st>>>(P);
+  kernel<<<dim3(c.grid, c.chunks), pit::TALL_THREADS, c.smem, st>>>(P);
   return cudaGetLastError();
 }
 
 template <int V>
 using Int = std::integral_constant<int, V>;
 
-// Calls f(Int<GEO>, Int<CPL>, Int<L4>) for the runtime (geo, cpl, l4).
+// Calls f(Int<GEO>, Int<CPL>, Int<NH>, Int<L4>) for the runtime values.
+template <typename G, typename C, typename H, typename F>
+cudaError_t with_l4(G g, C c, H h, int l4, F&& f) {
+  if (l4 == 1) return f(g, c, h, Int<1>{});
+  if (l4 == 2) return f(g, c, h, Int<2>{});
+  return f(g, c, h, Int<4>{});
+}
 template <typename G, typename C, typename F>
-cudaError_t with_l4(G g, C c, int l4, F&& f) {
-  if (l4 == 1) return f(g, c, Int<1>{});
-  if (l4 == 2) return f(g, c, Int<2>{});
-  return f(g, c, Int<4>{});
+cudaError_t with_heads(G g, C c, int nh, int l4, F&& f) {
+  if (nh == 1) return with_l4(g, c, Int<1>{}, l4, f);
+  return with_l4(g, c, Int<2>{}, l4, f);
 }
 template <typename G, typename F>
-cudaError_t with_cpl(G g, int cpl, int l4, F&& f) {
-  if (cpl == 4) return with_l4(g, Int<4>{}, l4, f);
-  if (cpl == 8) return with_l4(g, Int<8>{}, l4, f);
-  if (cpl == 16) return with_l4(g, Int<16>{}, l4, f);
-  return with_l4(g, Int<32>{}, l4, f);
+cudaError_t with_cpl(G g, int cpl, int nh, int l4, F&& f) {
+  if (cpl == 4) return with_heads(g, Int<4>{}, nh, l4, f);
+  if (cpl == 8) return with_heads(g, Int<8>{}, nh, l4, f);
+  if (cpl == 16) return with_heads(g, Int<16>{}, nh, l4, f);
+  return with_heads(g, Int<32>{}, nh, l4, f);
 }
 template <typename F>
-cudaError_t with_geo(int geo, int cpl, int l4, F&& f) {
-  if (geo == pit::GEO_EUCLID1) return with_cpl(Int<pit::GEO_EUCLID1>{}, cpl, l4, f);
-  if (geo == pit::GEO_EUCLID2) return with_cpl(Int<pit::GEO_EUCLID2>{}, cpl, l4, f);
-  if (geo == pit::GEO_PERIODIC1) return with_cpl(Int<pit::GEO_PERIODIC1>{}, cpl, l4, f);
-  return with_cpl(Int<pit::GEO_PERIODIC2>{}, cpl, l4, f);
+cudaError_t with_geo(int geo, int cpl, int nh, int l4, F&& f) {
+  if (geo == pit::GEO_EUCLID1) return with_cpl(Int<pit::GEO_EUCLID1>{}, cpl, nh, l4, f);
+  if (geo == pit::GEO_EUCLID2) return with_cpl(Int<pit::GEO_EUCLID2>{}, cpl, nh, l4, f);
+  if (geo == pit::GEO_PERIODIC1) return with_cpl(Int<pit::GEO_PERIODIC1>{}, cpl, nh, l4, f);
+  return with_cpl(Int<pit::GEO_PERIODIC2>{}, cpl, nh, l4, f);
 }
 
-cudaError_t coop_forward(int geo, const CoopPlan& plan, const pit::CoopParams& P, cudaStream_t st) {
-  return with_geo(geo, plan.cpl, plan.l4, [&](auto g, auto c, auto l) {
-    return coop_launch(pit::coop_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(l)::value>, plan, P, st);
+cudaError_t tall_forward(int geo, const TallPlan& plan, const pit::TallParams& P, cudaStream_t st) {
+  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
+    return tall_launch(pit::tall_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value, decltype(l)::value>, plan, P, st);
   });
 }
-cudaError_t coop_backward(int geo, const CoopPlan& plan, const pit::CoopParams& P, bool with_values, cudaStream_t st) {
-  return with_geo(geo, plan.cpl, plan.l4, [&](auto g, auto c, auto l) {
-    constexpr int G = decltype(g)::value, C = decltype(c)::value, L = decltype(l)::value;
-    return with_values ? coop_launch(pit::coop_bwd_kernel<G, C, L, true>, plan, P, st)
-                       : coop_launch(pit::coop_bwd_kernel<G, C, L, false>, plan, P, st);
+cudaError_t tall_backward(int geo, const TallPlan& plan, const pit::TallParams& P, bool with_values, cudaStream_t st) {
+  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
+    constexpr int G = decltype(g)::value, C = decltype(c)::value, NH = decltype(h)::value, L = decltype(l)::value;
+    return with_values ? tall_launch(pit::tall_bwd_kernel<G, C, NH, L, true>, plan, P, st)
+                       : tall_launch(pit::tall_bwd_kernel<G, C, NH, L, false>, plan, P, st);
   });
 }
 
@@ -403,14 +427,14 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     PIT_CUDA(cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(float), values, (size_t)p->dim * sizeof(float),
                                (size_t)p->dim * sizeof(float), (size_t)p->batch * p->n_in, cudaMemcpyDeviceToDevice, st));
   }
-  const CoopPlan plan = plan_coop(p, false, false);
+  const TallPlan plan = plan_tall_fwd(p);
   if (plan.ok) {
-    pit::CoopParams C = coop_params(p, plan, mesh_out, mesh_in, period, values, scale, stat);
+    pit::TallParams C = tall_params(p, plan, mesh_out, mesh_in, period, values, scale, stat);
     C.out = out;
     C.ld_out = ld_out;
     C.col_off = col_off;
     C.rowsum = rowsum;
-    PIT_CUDA(coop_forward(geo_of(p), plan, C, st));
+    PIT_CUDA(tall_forward(geo_of(p), plan, C, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return PIT_OK;
   }
@@ -457,15 +481,15 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   if (vec4 && (!aligned16(values) || !aligned16(d_out) || (d_values && !aligned16(d_values)) || (ld_out % 4) || (col_off % 4)))
     return fail(PIT_ERR_ARG, "values/d_out/d_values must be 16-byte aligned with ld_out, col_off multiples of 4 when D %% 4 == 0");
 
-  // Cooperative path (shared meshes, M <= 1024): one pass over d_out gives the scale gradient and, for a
+  // Tall path (shared meshes, M <= 1024, H <= 2): one pass over d_out gives the scale gradient and, for a
   // masked cross stage, the value gradient too.  A dense self stage keeps the value gradient on the
   // column-owner kernel below (every column is touched by every row, slots would not help).
   bool values_done = d_values == nullptr, scale_done = d_scale == nullptr;
   {
     const bool fuse_values = d_values && stat->masked && !accumulate_concat;
-    const CoopPlan plan = plan_coop(p, true, fuse_values);
+    const TallPlan plan = plan_tall_bwd(p, fuse_values);
     if (plan.ok && (d_scale || fuse_values)) {
-      pit::CoopParams C = coop_params(p, plan, mesh_out, mesh_in, period, values, scale, stat);
+      pit::TallParams C = tall_params(p, plan, mesh_out, mesh_in, period, values, scale, stat);
       C.rowsum = const_cast<float*>(rowsum);
       C.d_out = d_out;
       C.ld_out = ld_out;
@@ -474,7 +498,7 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
       C.d_scale = d_scale;
       if (d_scale) PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
       if (fuse_values) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
-      PIT_CUDA(coop_backward(geo, plan, C, fuse_values, st));
+      PIT_CUDA(tall_backward(geo, plan, C, fuse_values, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
       scale_done = true;
       if (fuse_values) values_done = true;
