@@ -11,6 +11,7 @@
 #include <type_traits>
 
 #include "tall_attention.cuh"
+#include "wide_attention.cuh"
 #include "local_attention.cuh"
 #include "rowstat.cuh"
 
@@ -320,6 +321,83 @@ cudaError_t tall_backward(int geo, const TallPlan& plan, const pit::TallParams& 
   });
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// "wide" kernels (shared meshes, few rows, huge column set, narrow values): the local encoder
+// ---------------------------------------------------------------------------------------------
+struct WidePlan {
+  bool ok;
+  int grid;
+  size_t smem;
+};
+
+WidePlan plan_wide(const pit_problem_t* p, const pit_rowstat_t* st) {
+  WidePlan w{};
+  const int width = p->batch * p->dim;
+  if (p->mesh_batched || !st->masked || p->n_head > pit::WIDE_MAX_H || width > pit::WIDE_MAX_WIDTH) return w;
+  if (p->n_in < 4096 || p->n_in < 8 * p->n_out) return w;
+  if ((int64_t)p->batch * p->n_in * p->dim >= (1ll << 31)) return w;
+  w.smem = ((size_t)p->n_out * pit::wide_row_words(p->n_head) + 2 * (size_t)width) * sizeof(float);
+  if (w.smem > 96 * 1024) return w;
+  const int64_t warps = ((int64_t)p->n_in + 32 * pit::WIDE_CPL - 1) / (32 * pit::WIDE_CPL);
+  w.grid = (int)((warps + pit::WIDE_WARPS - 1) / pit::WIDE_WARPS);
+  w.ok = true;
+  return w;
+}
+
+pit::WideParams wide_params(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                            const float* values, const float* scale, const pit_rowstat_t* st) {
+  pit::WideParams P{};
+  P.mesh_out = mesh_out;
+  P.mesh_in = mesh_in;
+  P.period = p->variant == PIT_EUCLID ? nullptr : period;
+  P.values = values;
+  P.scale = scale;
+  P.v_min = st->v_min;
+  P.v_lo = st->v_lo;
+  P.v_hi = st->v_hi;
+  P.weight = st->weight;
+  P.masked = st->masked;
+  P.B = p->batch;
+  P.H = p->n_head;
+  P.N = p->n_out;
+  P.M = p->n_in;
+  P.D = p->dim;
+  P.sd = p->space_dim;
+  P.width = p->batch * p->dim;
+  return P;
+}
+
+template <typename K>
+cudaError_t wide_launch(K kernel, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
+  if (w.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
+    if (e != cudaSuccess) return e;
+  }
+  kernel<<<w.grid, pit::WIDE_THREADS, w.smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <typename F>
+cudaError_t with_geo_heads(int geo, int nh, F&& f) {
+  auto heads = [&](auto g) { return nh == 1 ? f(g, Int<1>{}) : f(g, Int<2>{}); };
+  if (geo == pit::GEO_EUCLID1) return heads(Int<pit::GEO_EUCLID1>{});
+  if (geo == pit::GEO_EUCLID2) return heads(Int<pit::GEO_EUCLID2>{});
+  if (geo == pit::GEO_PERIODIC1) return heads(Int<pit::GEO_PERIODIC1>{});
+  return heads(Int<pit::GEO_PERIODIC2>{});
+}
+
+cudaError_t wide_forward(int geo, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
+  return with_geo_heads(geo, P.H, [&](auto g, auto h) {
+    return wide_launch(pit::wide_fwd_kernel<decltype(g)::value, decltype(h)::value>, w, P, st);
+  });
+}
+cudaError_t wide_dscale(int geo, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
+  return with_geo_heads(geo, P.H, [&](auto g, auto h) {
+    return wide_launch(pit::wide_dscale_kernel<decltype(g)::value, decltype(h)::value>, w, P, st);
+  });
+}
+
 // Sum of the per-row scale-gradient terms of one head (generic path): d_scale[h] = sum_rows rows[row*H + h].
 __global__ void reduce_scale_rows_kernel(const float* __restrict__ rows, int64_t n_rows, int H, float* __restrict__ d_scale) {
   __shared__ float red[32];
@@ -360,7 +438,7 @@ size_t pit_workspace_bytes(const pit_problem_t* p) {
   if (check_problem(p) != PIT_OK) return 0;
   const int64_t rows_total = (int64_t)(p->mesh_batched ? p->batch : 1) * p->n_out;
   const Shape f = make_shape(p, rows_total * p->n_head, p->n_in, true);
-  size_t fwd = f.n_split > 1 ? (size_t)f.items * f.width * sizeof(float) : 0;
+  size_t fwd = (f.n_split > 1 || (!p->mesh_batched && f.width <= pit::WIDE_MAX_WIDTH)) ? (size_t)f.items * f.width * sizeof(float) : 0;
   size_t bwd = (size_t)rows_total * p->n_head * 4 * sizeof(float);
   size_t need = fwd > bwd ? fwd : bwd;
   return need + 256;
@@ -444,6 +522,23 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
   P.col_off = col_off;
   P.rowsum = rowsum;
   P.split_len = s.split_len;
+  const WidePlan wide = plan_wide(p, stat);
+  if (wide.ok) {
+    const size_t need = (size_t)s.items * s.width * sizeof(float);
+    if (!workspace || workspace_bytes < need) return fail(PIT_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
+    P.partial = static_cast<float*>(workspace);
+    PIT_CUDA(cudaMemsetAsync(P.partial, 0, need, st));
+    PIT_CUDA(cudaMemsetAsync(rowsum, 0, (size_t)s.items * sizeof(float), st));
+    pit::WideParams W = wide_params(p, mesh_out, mesh_in, period, values, scale, stat);
+    W.partial = P.partial;
+    W.rowsum = rowsum;
+    PIT_CUDA(wide_forward(geo_of(p), wide, W, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const int64_t total = s.items * s.width;
+    pit::posatt_fwd_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P);
+    PIT_LAUNCHED();
+    return PIT_OK;
+  }
   if (s.n_split > 1) {
     const size_t need = (size_t)s.items * s.width * sizeof(float);
     if (!workspace || workspace_bytes < need) return fail(PIT_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
@@ -522,9 +617,20 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
     float* rows = P.dscale_terms + (size_t)s.items * 3;
     P.split_len = s.split_len;
     PIT_CUDA(cudaMemsetAsync(P.dscale_terms, 0, (size_t)s.items * 3 * sizeof(float), st));
-    const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
-    PIT_DISPATCH(pit::posatt_dscale_kernel, geo, s.vec, s.a, <<<grid, block, 0, st>>>(P));
-    PIT_LAUNCHED();
+    const WidePlan wide = plan_wide(p, stat);
+    if (wide.ok) {
+      pit::WideParams W = wide_params(p, mesh_out, mesh_in, period, values, scale, stat);
+      W.d_out = d_out;
+      W.ld_out = ld_out;
+      W.col_off = col_off;
+      W.dscale_terms = P.dscale_terms;
+      PIT_CUDA(wide_dscale(geo, wide, W, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+      const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
+      PIT_DISPATCH(pit::posatt_dscale_kernel, geo, s.vec, s.a, <<<grid, block, 0, st>>>(P));
+      PIT_LAUNCHED();
+    }
     pit::posatt_dscale_finalize_kernel<<<(unsigned)((s.items + 255) / 256), 256, 0, st>>>(P, rows);
     PIT_LAUNCHED();
     reduce_scale_rows_kernel<<<p->n_head, 512, 0, st>>>(rows, rows_total, p->n_head, d_scale);

@@ -1,0 +1,258 @@
+// K1w: position-attention for shared meshes with FEW output rows and a HUGE column set with narrow values
+// (the local encoder: N = 256 latent points, M = 177 241 mesh points, B*D = 24 at Darcy-421).
+//
+// Roles are transposed with respect to the tall kernels: a lane owns CPL columns for the kernel's whole
+// life (coordinates in registers) and the warp walks over ALL rows, whose per-row constants (point, soft-max
+// shift and cut of every head) sit in a shared-memory table built once per CTA.  The sweep touches no global
+// memory.  Only ~2 % of the (row, column) pairs are kept and they are spatially clustered, so a warp finds
+// something to do for ~5 % of the rows; for those the kept lanes gather their value rows, and the per-row sums
+// are combined across lanes with shuffles and across warps with a handful of fp32 REDs (the soft-max shift
+// is known in advance, so partial sums need no rescaling).
+//
+//   wide_fwd_kernel     partial[(row,h), e] += sum_j P_hj U[j,e];  rowsum[(h,row)] += sum_j P_hj   (+ finalize)
+//   wide_dscale_kernel  per (row,h): A += sum_j P d2 dP_j, Bq += sum_j P dP_j, m += sum_j P d2 with
+//                       dP_j = <dO[row,h,:], U[j,:]> a lane-local dot product          (+ the generic finalize)
+#pragma once
+#include "geometry.cuh"
+
+namespace pit {
+
+constexpr int WIDE_THREADS = 128;
+constexpr int WIDE_WARPS = WIDE_THREADS / 32;
+constexpr int WIDE_CPL = 4;       // columns per lane: 128 columns per warp
+constexpr int WIDE_MAX_WIDTH = 32;  // B*D scalars per value row
+constexpr int WIDE_MAX_H = 2;
+
+struct WideParams {
+  const float* mesh_out;  // [N,sd]
+  const float* mesh_in;   // [M,sd]
+  const float* period;
+  const float* values;  // [B,M,D]
+  const float* scale;   // [H]
+  const float* v_min;
+  const float* v_lo;
+  const float* v_hi;
+  float weight;
+  int masked;
+  int B, H, N, M, D, sd;
+  int width;  // B*D
+  // forward
+  float* partial;  // [N*H, width] zero-initialised
+  float* rowsum;   // [H,N]       zero-initialised
+  // backward
+  const float* d_out;
+  int64_t ld_out, col_off;
+  float* dscale_terms;  // [N*H,3] zero-initialised
+};
+
+// Row table entry: x, y, then per head (top, cut).
+__host__ __device__ inline int wide_row_words(int H) { return 2 + 2 * H; }
+
+template <int GEO>
+__device__ __forceinline__ void wide_build_rows(const WideParams& P, float* rowtab, int* val_off, int* g_off) {
+  const int rw = wide_row_words(P.H);
+  for (int r = threadIdx.x; r < P.N; r += WIDE_THREADS) {
+    const Point<GEO> o = load_point<GEO>(P.mesh_out, r, P.sd);
+    float* t = rowtab + (size_t)r * rw;
+    t[0] = o.x;
+    t[1] = o.y;
+    const float vmin = __ldg(P.v_min + r);
+    for (int h = 0; h < P.H; ++h) {
+      const float s = __ldg(P.scale + h);
+      t[2 + 2 * h] = __fmul_rn(vmin, s);
+      t[3 + 2 * h] = P.masked ? head_threshold(__ldg(P.v_lo + r), __ldg(P.v_hi + r), s, P.weight) : INFINITY;
+    }
+  }
+  for (int e = threadIdx.x; e < P.width; e += WIDE_THREADS) {
+    const int b = e / P.D, d = e - b * P.D;
+    val_off[e] = b * P.M * P.D + d;  // host guarantees B*M*D < 2^31
+    if (g_off) g_off[e] = d;         // + b*N*ld_out handled with 64-bit arithmetic at use
+  }
+}
+
+template <int GEO, int NH>
+__global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams P) {
+  extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+  const int rw = wide_row_words(NH);
+  float* rowtab = reinterpret_cast<float*>(wide_smem_raw);
+  int* val_off = reinterpret_cast<int*>(rowtab + (size_t)P.N * rw);
+  wide_build_rows<GEO>(P, rowtab, val_off, nullptr);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float period = P.period ? __ldg(P.period) : 0.f;
+  const int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL);
+  if (base >= P.M) return;
+  Point<GEO> col[WIDE_CPL];
+  int jcol[WIDE_CPL];
+#pragma unroll
+  for (int c = 0; c < WIDE_CPL; ++c) {
+    const int64_t j = base + c * 32 + lane;
+    jcol[c] = j < P.M ? (int)j : -1;
+    col[c] = load_point<GEO>(P.mesh_in, j < P.M ? j : 0, P.sd);
+  }
+  float s[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
+
+  for (int r = 0; r < P.N; ++r) {
+    const float* t = rowtab + (size_t)r * rw;
+    Point<GEO> o;
+    o.x = t[0];
+    o.y = t[1];
+    float p[WIDE_CPL][NH];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < WIDE_CPL; ++c) {
+      const float d2 = dist2<GEO>(o, col[c], period);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        p[c][h] = 0.f;
+        if (jcol[c] >= 0) {
+          const float sc = __fmul_rn(d2, s[h]);
+          if (sc <= t[3 + 2 * h]) p[c][h] = expf(__fsub_rn(t[2 + 2 * h], sc));
+        }
+        any = any || (p[c][h] > 0.f);
+      }
+    }
+    if (!__any_sync(FULL, any)) continue;
+    // ---- rare path: this warp holds kept columns of row r ----
+    float lsum[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      lsum[h] = 0.f;
+#pragma unroll
+      for (int c = 0; c < WIDE_CPL; ++c) lsum[h] += p[c][h];
+      lsum[h] = warp_sum(lsum[h]);
+    }
+    float mine[NH];  // lane e ends up with element e of the warp's partial sum
+#pragma unroll
+    for (int h = 0; h < NH; ++h) mine[h] = 0.f;
+    for (int e = 0; e < P.width; ++e) {
+      float part[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) part[h] = 0.f;
+      if (any) {
+        const int off = val_off[e];
+#pragma unroll
+        for (int c = 0; c < WIDE_CPL; ++c) {
+          bool kept = false;
+#pragma unroll
+          for (int h = 0; h < NH; ++h) kept = kept || (p[c][h] > 0.f);
+          if (kept) {
+            const float u = __ldg(P.values + off + (int64_t)jcol[c] * P.D);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) part[h] = fmaf(p[c][h], u, part[h]);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float v = warp_sum(part[h]);
+        if (lane == e) mine[h] = v;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      if (lsum[h] > 0.f) {
+        if (lane < P.width) atomicAdd(P.partial + ((int64_t)r * NH + h) * P.width + lane, mine[h]);
+        if (lane == 0) atomicAdd(P.rowsum + (int64_t)h * P.N + r, lsum[h]);
+      }
+    }
+  }
+}
+
+template <int GEO, int NH>
+__global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WideParams P) {
+  extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+  const int rw = wide_row_words(NH);
+  float* rowtab = reinterpret_cast<float*>(wide_smem_raw);
+  int* val_off = reinterpret_cast<int*>(rowtab + (size_t)P.N * rw);
+  int* g_off = val_off + P.width;
+  wide_build_rows<GEO>(P, rowtab, val_off, g_off);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float period = P.period ? __ldg(P.period) : 0.f;
+  const int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL);
+  if (base >= P.M) return;
+  Point<GEO> col[WIDE_CPL];
+  int jcol[WIDE_CPL];
+#pragma unroll
+  for (int c = 0; c < WIDE_CPL; ++c) {
+    const int64_t j = base + c * 32 + lane;
+    jcol[c] = j < P.M ? (int)j : -1;
+    col[c] = load_point<GEO>(P.mesh_in, j < P.M ? j : 0, P.sd);
+  }
+  float s[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
+
+  for (int r = 0; r < P.N; ++r) {
+    const float* t = rowtab + (size_t)r * rw;
+    Point<GEO> o;
+    o.x = t[0];
+    o.y = t[1];
+    float p[WIDE_CPL][NH], d2c[WIDE_CPL];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < WIDE_CPL; ++c) {
+      d2c[c] = dist2<GEO>(o, col[c], period);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        p[c][h] = 0.f;
+        if (jcol[c] >= 0) {
+          const float sc = __fmul_rn(d2c[c], s[h]);
+          if (sc <= t[3 + 2 * h]) p[c][h] = expf(__fsub_rn(t[2 + 2 * h], sc));
+        }
+        any = any || (p[c][h] > 0.f);
+      }
+    }
+    if (!__any_sync(FULL, any)) continue;
+    float a_sum[NH], b_sum[NH], m_sum[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) a_sum[h] = b_sum[h] = m_sum[h] = 0.f;
+    if (any) {
+#pragma unroll
+      for (int c = 0; c < WIDE_CPL; ++c) {
+        bool kept = false;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) kept = kept || (p[c][h] > 0.f);
+        if (!kept) continue;
+        float dp[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) dp[h] = 0.f;
+        for (int e = 0; e < P.width; ++e) {
+          const float u = __ldg(P.values + val_off[e] + (int64_t)jcol[c] * P.D);
+          const int b = e / P.D;
+          const float* grow = P.d_out + ((int64_t)b * P.N + r) * P.ld_out + P.col_off + g_off[e];
+#pragma unroll
+          for (int h = 0; h < NH; ++h) dp[h] = fmaf(__ldg(grow + (int64_t)h * P.D), u, dp[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float pd = p[c][h] * d2c[c];
+          a_sum[h] = fmaf(pd, dp[h], a_sum[h]);
+          b_sum[h] = fmaf(p[c][h], dp[h], b_sum[h]);
+          m_sum[h] += pd;
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float kept_w = 0.f;
+#pragma unroll
+      for (int c = 0; c < WIDE_CPL; ++c) kept_w += p[c][h];
+      kept_w = warp_sum(kept_w);
+      const float a = warp_sum(a_sum[h]), bq = warp_sum(b_sum[h]), m = warp_sum(m_sum[h]);
+      if (lane == 0 && kept_w > 0.f) {
+        float* dst = P.dscale_terms + ((int64_t)r * NH + h) * 3;
+        atomicAdd(dst + 0, a);
+        atomicAdd(dst + 1, bq);
+        atomicAdd(dst + 2, m);
+      }
+    }
+  }
+}
+
+}  // namespace pit
