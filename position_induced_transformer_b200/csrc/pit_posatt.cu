@@ -338,7 +338,7 @@ WidePlan plan_wide(const pit_problem_t* p, const pit_rowstat_t* st) {
   if (p->n_in < 4096 || p->n_in < 8 * p->n_out) return w;
   if ((int64_t)p->batch * p->n_in * p->dim >= (1ll << 31)) return w;
   w.smem = ((size_t)p->n_out * pit::wide_row_words(p->n_head) + 2 * (size_t)width) * sizeof(float);
-  if (w.smem > 96 * 1024) return w;
+  if (w.smem + (size_t)p->n_out * p->n_head * 32 * sizeof(float) > 160 * 1024) return w;
   const int64_t warps = ((int64_t)p->n_in + 32 * pit::WIDE_CPL - 1) / (32 * pit::WIDE_CPL);
   w.grid = (int)((warps + pit::WIDE_WARPS - 1) / pit::WIDE_WARPS);
   w.ok = true;
@@ -378,9 +378,17 @@ cudaError_t wide_launch(K kernel, const WidePlan& w, const pit::WideParams& P, c
   return cudaGetLastError();
 }
 
+int wide_pad(int width) { return width <= 8 ? 8 : (width <= 16 ? 16 : (width <= 24 ? 24 : 32)); }
+
 template <typename F>
-cudaError_t with_geo_heads(int geo, int nh, F&& f) {
-  auto heads = [&](auto g) { return nh == 1 ? f(g, Int<1>{}) : f(g, Int<2>{}); };
+cudaError_t with_geo_heads_pad(int geo, int nh, int wpad, F&& f) {
+  auto pad = [&](auto g, auto h) {
+    if (wpad == 8) return f(g, h, Int<8>{});
+    if (wpad == 16) return f(g, h, Int<16>{});
+    if (wpad == 24) return f(g, h, Int<24>{});
+    return f(g, h, Int<32>{});
+  };
+  auto heads = [&](auto g) { return nh == 1 ? pad(g, Int<1>{}) : pad(g, Int<2>{}); };
   if (geo == pit::GEO_EUCLID1) return heads(Int<pit::GEO_EUCLID1>{});
   if (geo == pit::GEO_EUCLID2) return heads(Int<pit::GEO_EUCLID2>{});
   if (geo == pit::GEO_PERIODIC1) return heads(Int<pit::GEO_PERIODIC1>{});
@@ -388,13 +396,15 @@ cudaError_t with_geo_heads(int geo, int nh, F&& f) {
 }
 
 cudaError_t wide_forward(int geo, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
-  return with_geo_heads(geo, P.H, [&](auto g, auto h) {
-    return wide_launch(pit::wide_fwd_kernel<decltype(g)::value, decltype(h)::value>, w, P, st);
+  return with_geo_heads_pad(geo, P.H, wide_pad(P.width), [&](auto g, auto h, auto wp) {
+    return wide_launch(pit::wide_fwd_kernel<decltype(g)::value, decltype(h)::value, decltype(wp)::value>, w, P, st);
   });
 }
 cudaError_t wide_dscale(int geo, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
-  return with_geo_heads(geo, P.H, [&](auto g, auto h) {
-    return wide_launch(pit::wide_dscale_kernel<decltype(g)::value, decltype(h)::value>, w, P, st);
+  WidePlan wb = w;  // the backward also keeps the upstream-gradient rows in shared memory
+  wb.smem += (size_t)P.N * P.H * wide_pad(P.width) * sizeof(float);
+  return with_geo_heads_pad(geo, P.H, wide_pad(P.width), [&](auto g, auto h, auto wp) {
+    return wide_launch(pit::wide_dscale_kernel<decltype(g)::value, decltype(h)::value, decltype(wp)::value>, wb, P, st);
   });
 }
 

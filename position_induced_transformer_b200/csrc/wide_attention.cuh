@@ -70,7 +70,7 @@ __device__ __forceinline__ void wide_build_rows(const WideParams& P, float* rowt
   }
 }
 
-template <int GEO, int NH>
+template <int GEO, int NH, int WPAD>
 __global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams P) {
   extern __shared__ __align__(16) unsigned char wide_smem_raw[];
   const int rw = wide_row_words(NH);
@@ -94,6 +94,13 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams
   float s[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
+  // the lane's own value rows stay in registers: u[c][e] = U[b_e, j_c, d_e]
+  float u[WIDE_CPL][WPAD];
+#pragma unroll
+  for (int c = 0; c < WIDE_CPL; ++c)
+#pragma unroll
+    for (int e = 0; e < WPAD; ++e)
+      u[c][e] = (e < P.width && jcol[c] >= 0) ? __ldg(P.values + val_off[e] + (int64_t)jcol[c] * P.D) : 0.f;
 
   for (int r = 0; r < P.N; ++r) {
     const float* t = rowtab + (size_t)r * rw;
@@ -116,60 +123,49 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams
       }
     }
     if (!__any_sync(FULL, any)) continue;
-    // ---- rare path: this warp holds kept columns of row r ----
-    float lsum[NH];
+    // ---- rare path: this warp holds kept columns of row r; everything needed is in registers ----
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
-      lsum[h] = 0.f;
+      float lsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < WIDE_CPL; ++c) lsum[h] += p[c][h];
-      lsum[h] = warp_sum(lsum[h]);
-    }
-    float mine[NH];  // lane e ends up with element e of the warp's partial sum
+      for (int c = 0; c < WIDE_CPL; ++c) lsum += p[c][h];
+      lsum = warp_sum(lsum);
+      if (lsum > 0.f) {  // warp-uniform
+        float mine = 0.f;  // lane e ends up with element e of the warp's partial sum
 #pragma unroll
-    for (int h = 0; h < NH; ++h) mine[h] = 0.f;
-    for (int e = 0; e < P.width; ++e) {
-      float part[NH];
+        for (int e = 0; e < WPAD; ++e) {
+          float part = 0.f;
 #pragma unroll
-      for (int h = 0; h < NH; ++h) part[h] = 0.f;
-      if (any) {
-        const int off = val_off[e];
-#pragma unroll
-        for (int c = 0; c < WIDE_CPL; ++c) {
-          bool kept = false;
-#pragma unroll
-          for (int h = 0; h < NH; ++h) kept = kept || (p[c][h] > 0.f);
-          if (kept) {
-            const float u = __ldg(P.values + off + (int64_t)jcol[c] * P.D);
-#pragma unroll
-            for (int h = 0; h < NH; ++h) part[h] = fmaf(p[c][h], u, part[h]);
-          }
+          for (int c = 0; c < WIDE_CPL; ++c) part = fmaf(p[c][h], u[c][e], part);
+          part = warp_sum(part);
+          if (lane == e) mine = part;
         }
-      }
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        const float v = warp_sum(part[h]);
-        if (lane == e) mine[h] = v;
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      if (lsum[h] > 0.f) {
-        if (lane < P.width) atomicAdd(P.partial + ((int64_t)r * NH + h) * P.width + lane, mine[h]);
-        if (lane == 0) atomicAdd(P.rowsum + (int64_t)h * P.N + r, lsum[h]);
+        if (lane < P.width) atomicAdd(P.partial + ((int64_t)r * NH + h) * P.width + lane, mine);
+        if (lane == 0) atomicAdd(P.rowsum + (int64_t)h * P.N + r, lsum);
       }
     }
   }
 }
 
-template <int GEO, int NH>
+template <int GEO, int NH, int WPAD>
 __global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WideParams P) {
   extern __shared__ __align__(16) unsigned char wide_smem_raw[];
   const int rw = wide_row_words(NH);
   float* rowtab = reinterpret_cast<float*>(wide_smem_raw);
   int* val_off = reinterpret_cast<int*>(rowtab + (size_t)P.N * rw);
-  int* g_off = val_off + P.width;
-  wide_build_rows<GEO>(P, rowtab, val_off, g_off);
+  float* gtab = reinterpret_cast<float*>(val_off + P.width);  // [N][NH][WPAD] upstream gradient rows
+  wide_build_rows<GEO>(P, rowtab, val_off, nullptr);
+  for (int idx = threadIdx.x; idx < P.N * NH * WPAD; idx += WIDE_THREADS) {
+    const int e = idx % WPAD;
+    const int h = (idx / WPAD) % NH;
+    const int r = idx / (WPAD * NH);
+    float g = 0.f;
+    if (e < P.width) {
+      const int b = e / P.D, d = e - b * P.D;
+      g = __ldg(P.d_out + ((int64_t)b * P.N + r) * P.ld_out + P.col_off + (int64_t)h * P.D + d);
+    }
+    gtab[idx] = g;
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,6 +183,12 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WidePar
   float s[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
+  float u[WIDE_CPL][WPAD];
+#pragma unroll
+  for (int c = 0; c < WIDE_CPL; ++c)
+#pragma unroll
+    for (int e = 0; e < WPAD; ++e)
+      u[c][e] = (e < P.width && jcol[c] >= 0) ? __ldg(P.values + val_off[e] + (int64_t)jcol[c] * P.D) : 0.f;
 
   for (int r = 0; r < P.N; ++r) {
     const float* t = rowtab + (size_t)r * rw;
@@ -209,47 +211,34 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WidePar
       }
     }
     if (!__any_sync(FULL, any)) continue;
-    float a_sum[NH], b_sum[NH], m_sum[NH];
-#pragma unroll
-    for (int h = 0; h < NH; ++h) a_sum[h] = b_sum[h] = m_sum[h] = 0.f;
-    if (any) {
-#pragma unroll
-      for (int c = 0; c < WIDE_CPL; ++c) {
-        bool kept = false;
-#pragma unroll
-        for (int h = 0; h < NH; ++h) kept = kept || (p[c][h] > 0.f);
-        if (!kept) continue;
-        float dp[NH];
-#pragma unroll
-        for (int h = 0; h < NH; ++h) dp[h] = 0.f;
-        for (int e = 0; e < P.width; ++e) {
-          const float u = __ldg(P.values + val_off[e] + (int64_t)jcol[c] * P.D);
-          const int b = e / P.D;
-          const float* grow = P.d_out + ((int64_t)b * P.N + r) * P.ld_out + P.col_off + g_off[e];
-#pragma unroll
-          for (int h = 0; h < NH; ++h) dp[h] = fmaf(__ldg(grow + (int64_t)h * P.D), u, dp[h]);
-        }
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          const float pd = p[c][h] * d2c[c];
-          a_sum[h] = fmaf(pd, dp[h], a_sum[h]);
-          b_sum[h] = fmaf(p[c][h], dp[h], b_sum[h]);
-          m_sum[h] += pd;
-        }
-      }
-    }
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
       float kept_w = 0.f;
 #pragma unroll
       for (int c = 0; c < WIDE_CPL; ++c) kept_w += p[c][h];
       kept_w = warp_sum(kept_w);
-      const float a = warp_sum(a_sum[h]), bq = warp_sum(b_sum[h]), m = warp_sum(m_sum[h]);
-      if (lane == 0 && kept_w > 0.f) {
-        float* dst = P.dscale_terms + ((int64_t)r * NH + h) * 3;
-        atomicAdd(dst + 0, a);
-        atomicAdd(dst + 1, bq);
-        atomicAdd(dst + 2, m);
+      if (kept_w > 0.f) {  // warp-uniform
+        const float* g = gtab + ((size_t)r * NH + h) * WPAD;
+        float a_sum = 0.f, b_sum = 0.f, m_sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < WIDE_CPL; ++c) {
+          float dp = 0.f;  // <dO[row,h,:], U[j_c,:]>
+#pragma unroll
+          for (int e = 0; e < WPAD; ++e) dp = fmaf(g[e], u[c][e], dp);
+          const float pd = p[c][h] * d2c[c];
+          a_sum = fmaf(pd, dp, a_sum);
+          b_sum = fmaf(p[c][h], dp, b_sum);
+          m_sum += pd;
+        }
+        a_sum = warp_sum(a_sum);
+        b_sum = warp_sum(b_sum);
+        m_sum = warp_sum(m_sum);
+        if (lane == 0) {
+          float* dst = P.dscale_terms + ((int64_t)r * NH + h) * 3;
+          atomicAdd(dst + 0, a_sum);
+          atomicAdd(dst + 1, b_sum);
+          atomicAdd(dst + 2, m_sum);
+        }
       }
     }
   }
