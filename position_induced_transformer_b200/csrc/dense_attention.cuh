@@ -1,0 +1,459 @@
+// K2: dense (global, locality >= 1) position-attention on the 5th-generation tensor cores.
+//
+// A global stage is a genuine dense contraction  O[i, c] = sum_j P[i, j] V[j, c]  with
+// P[i, j] = exp(s_h (v_min_i - d2_ij)) generated on the fly from coordinates (flash style: P never
+// exists in HBM) and V the value features of every sample side by side (shared meshes) or of one
+// sample (per-sample meshes).  The tile loop is a warp-specialised producer/consumer pipeline:
+//
+//   warps 0-3  "generators": thread t owns tile row t; per K block it evaluates 32 weights from the
+//              coordinates (exp2 with the row's known shift, so no online rescaling), splits each into a
+//              TF32 high part and an fp32 residual, and writes both as UMMA operand A (K-major,
+//              128-byte swizzle) into shared memory; it also keeps the fp32 row sum.
+//   warps 4-7  "stagers": stream the [32 x NV] value block from global memory with 128-bit loads,
+//              split hi/lo the same way, and lay it out as UMMA operand B (MN-major, 128-byte swizzle).
+//   warp 8     one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=NV, K=8): hi*hi + lo*hi + hi*lo,
+//              i.e. 3xTF32 with fp32 accumulation in TMEM (error ~2^-21, inside the 1e-5 parity budget),
+//              then tcgen05.commit's the stage back to the producers through an mbarrier.
+//   warps 0-3  epilogue: tcgen05.ld the accumulator rows out of TMEM, normalise by the row sum, store.
+//
+// Operands cannot come through TMA here: both need the in-register hi/lo split (and A is computed, not
+// loaded), so the stage hand-off is mbarrier + fence.proxy.async rather than a TMA transaction count.
+//
+// The same pipeline serves the backward of a dense stage:
+//   DENSE_DSCALE   two A operands (P and P*d2) against the same V block -> accumulators O and W in TMEM;
+//                  epilogue forms -sum_e dO_e (W_e - (m/l) O_e) / l per row and reduces it per head;
+//   DENSE_DVALUES  roles swapped: tile rows are columns j, the K loop runs over rows i of every head,
+//                  A = P^T / l_i, B = dO[i, (b,d)]; epilogue adds the concat pass-through and stores dU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "geometry.cuh"
+
+namespace pit {
+
+constexpr int DENSE_ROWS = 128;  // UMMA M
+constexpr int DENSE_KB = 32;     // reduction entries per K block = one 128-byte swizzle row of tf32
+constexpr int DENSE_GEN_THREADS = 128;
+constexpr int DENSE_STAGE_THREADS = 128;
+constexpr int DENSE_THREADS = DENSE_GEN_THREADS + DENSE_STAGE_THREADS + 32;
+constexpr int DENSE_STAGES = 2;
+
+enum : int { DENSE_FWD = 0, DENSE_DSCALE = 1, DENSE_DVALUES = 2 };
+
+struct DenseParams {
+  // geometry: "owner" points index the tile rows, "reduced" points index the K loop
+  const float* mesh_own;  // [(B),n_own,sd]
+  const float* mesh_red;  // [(B),n_red,sd]
+  const float* period;
+  const float* scale;   // [H]
+  const float* v_min;   // [(B),N] indexed by attention row i
+  const float* rowsum;  // [(B),H,N] (backward modes)
+  int n_own, n_red;     // FWD/DSCALE: N, M ; DVALUES: M, N
+  int N, M, B, H, D, sd, mesh_batched;
+  int width;            // value columns in total: mesh_batched ? D : B*D
+  // operand B source: element (k, n) at  b_src + b_off + (n / D) * b_bstride + n % D + k * b_kstride (+ h * b_hstride)
+  const float* b_src;
+  int64_t b_kstride, b_bstride, b_hstride, b_off;
+  // FWD
+  float* out;
+  int64_t ld_out, col_off;
+  float* rowsum_out;
+  // DSCALE
+  const float* d_out;
+  float* d_scale;  // [H] zero-initialised
+  // DVALUES
+  float* d_values;  // [B,M,D]
+  int add_concat;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS));
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread for the CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier when every tcgen05 operation issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread l of warp w reads TMEM lane 32*(w%4)+l.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor), SWIZZLE_128B, version 1.
+//   K-major  operand (A): rows of 128 bytes (32 tf32 along K), 8-row groups 1024 bytes apart (SBO); LBO unused (1).
+//   MN-major operand (B): atoms of 8 K-rows x 128 bytes (32 tf32 along N); next atom along N at LBO, next 8 K-rows at SBO.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (InstrDescriptor): D=F32, A=B=TF32, A K-major, B MN-major, M=128, N=NV.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(DENSE_ROWS >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Byte offset of the 16-byte chunk (row r, chunk c of 8) inside a K-major 128B-swizzled tile of 128 rows.
+__device__ __forceinline__ uint32_t a_chunk_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+// Byte offset of the 16-byte chunk (k row of 32, n chunk nc of NV/4) inside an MN-major 128B-swizzled [32 x NV] tile:
+// atom index = (nc / 8) * 4 + k / 8, so LBO (next 32 columns) = 4096 bytes and SBO (next 8 k rows) = 1024 bytes.
+__device__ __forceinline__ uint32_t b_chunk_offset(int k, int nc) {
+  return (uint32_t)((((nc >> 3) << 2) + (k >> 3)) * 1024 + (k & 7) * 128 + (((nc & 7) ^ (k & 7)) << 4));
+}
+
+template <int MODE, int NV>
+struct DenseSmem {
+  static constexpr int A_TILES = (MODE == DENSE_DSCALE) ? 4 : 2;  // hi, lo (and the d2-weighted pair)
+  static constexpr int A_BYTES = DENSE_ROWS * DENSE_KB * 4;        // 16 KB
+  static constexpr int B_BYTES = DENSE_KB * NV * 4;
+  static constexpr int STAGE_BYTES = A_TILES * A_BYTES + 2 * B_BYTES;
+  static constexpr int TOTAL = DENSE_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 4 * 32 * 16 /*reduced-point tables*/ + 256;
+};
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <int GEO, int MODE, int NV>
+__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const DenseParams P) {
+  using L = DenseSmem<MODE, NV>;
+  constexpr int ACC_COLS = (MODE == DENSE_DSCALE) ? 2 * NV : NV;
+  constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+  extern __shared__ unsigned char dense_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[DENSE_STAGES], empty_bar[DENSE_STAGES], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float red[DENSE_GEN_THREADS / 32];
+
+  const uint32_t raw = smem_u32(dense_smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+  unsigned char* tiles_ptr = dense_smem_raw + (tiles - raw);
+  float4* red_pts = reinterpret_cast<float4*>(tiles_ptr + DENSE_STAGES * L::STAGE_BYTES);  // [4 warps][32] (x, y, vmin*, post)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.z;
+  const int h_fixed = z % P.H;                       // FWD/DSCALE: the head of this CTA
+  const int bm = P.mesh_batched ? z / P.H : 0;       // sample (per-sample meshes)
+  const int bm_dv = P.mesh_batched ? z : 0;          // DVALUES: grid.z = samples only
+  const int own0 = blockIdx.x * DENSE_ROWS;
+  const int n0 = blockIdx.y * NV;
+  const float period = P.period ? __ldg(P.period) : 0.f;
+  const int sample = (MODE == DENSE_DVALUES) ? bm_dv : bm;
+
+  if (tid == 0) {
+    for (int s = 0; s < DENSE_STAGES; ++s) {
+      mbar_init(&full_bar[s], DENSE_GEN_THREADS + DENSE_STAGE_THREADS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int heads_in_k = (MODE == DENSE_DVALUES) ? P.H : 1;
+  const int kb_per_head = (P.n_red + DENSE_KB - 1) / DENSE_KB;
+  const int n_kb = kb_per_head * heads_in_k;
+
+  if (warp < 4) {
+    // =========================== generators (and epilogue) ===========================
+    const int r = tid;  // tile row
+    const int own = own0 + r;
+    const bool own_ok = own < P.n_own;
+    const float* mesh_own = P.mesh_own + (int64_t)sample * P.n_own * P.sd;
+    const float* mesh_red = P.mesh_red + (int64_t)sample * P.n_red * P.sd;
+    const Point<GEO> me = load_point<GEO>(mesh_own, own_ok ? own : 0, P.sd);
+    float4* my_pts = red_pts + warp * 32;
+    const float LOG2E = 1.4426950408889634f;
+    // FWD/DSCALE: the row's own shift; DVALUES: per reduced row, read from the table
+    float own_vmin = 0.f;
+    if (MODE != DENSE_DVALUES) own_vmin = __ldg(P.v_min + (int64_t)sample * P.N + (own_ok ? own : 0));
+    float lsum = 0.f, msum = 0.f;
+
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % DENSE_STAGES;
+      const uint32_t use = kb / DENSE_STAGES;
+      const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : h_fixed;
+      const int k0 = (kb % kb_per_head) * DENSE_KB;
+      const float sc2 = __ldg(P.scale + h) * LOG2E;
+      // the 32 reduced points of this block (per-warp copy: no block-level sync needed)
+      {
+        const int k = k0 + lane;
+        const bool ok = k < P.n_red;
+        const Point<GEO> q = load_point<GEO>(mesh_red, ok ? k : 0, P.sd);
+        float vm = 0.f, post = ok ? 1.f : 0.f;
+        if (MODE == DENSE_DVALUES && ok) {
+          vm = __ldg(P.v_min + (int64_t)sample * P.N + k);
+          post = 1.f / __ldg(P.rowsum + ((int64_t)sample * P.H + h) * P.N + k);
+        }
+        __syncwarp();
+        my_pts[lane] = make_float4(q.x, q.y, vm, post);
+        __syncwarp();
+      }
+      mbar_wait(&empty_bar[s], (use & 1) ^ 1);
+      unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float hi[4], lo[4], hid[4], lod[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 q = my_pts[c * 4 + e];
+          Point<GEO> other;
+          other.x = q.x;
+          other.y = q.y;
+          const float d2 = (MODE == DENSE_DVALUES) ? dist2<GEO>(other, me, period) : dist2<GEO>(me, other, period);
+          const float vm = (MODE == DENSE_DVALUES) ? q.z : own_vmin;
+          float p = exp2f((vm - d2) * sc2) * q.w;
+          if (!own_ok) p = 0.f;
+          lsum += p;
+          hi[e] = tf32_hi(p);
+          lo[e] = p - hi[e];
+          if (MODE == DENSE_DSCALE) {
+            const float pd = p * d2;
+            msum += pd;
+            hid[e] = tf32_hi(pd);
+            lod[e] = pd - hid[e];
+          }
+        }
+        const uint32_t off = a_chunk_offset(r, c);
+        *reinterpret_cast<float4*>(stage + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(stage + L::A_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        if (MODE == DENSE_DSCALE) {
+          *reinterpret_cast<float4*>(stage + 2 * L::A_BYTES + off) = make_float4(hid[0], hid[1], hid[2], hid[3]);
+          *reinterpret_cast<float4*>(stage + 3 * L::A_BYTES + off) = make_float4(lod[0], lod[1], lod[2], lod[3]);
+        }
+      }
+      fence_async_shared();
+      mbar_arrive(&full_bar[s]);
+    }
+
+    // ------------------------------- epilogue -------------------------------
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (MODE == DENSE_FWD) {
+      const float inv_l = 1.f / lsum;
+      if (own_ok && blockIdx.y == 0) P.rowsum_out[((int64_t)sample * P.H + h_fixed) * P.N + own] = lsum;
+      for (int c0 = 0; c0 < NV; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_addr + c0, v);  // warp-collective: every lane takes part
+        if (own_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const int n = n0 + c0 + e;
+            if (n < P.width) {
+              const int b = P.mesh_batched ? sample : n / P.D;
+              const int d = P.mesh_batched ? n : n - b * P.D;
+              float* dst = P.out + ((int64_t)b * P.N + own) * P.ld_out + P.col_off + (int64_t)h_fixed * P.D + d;
+              *reinterpret_cast<float4*>(dst) = make_float4(v[e] * inv_l, v[e + 1] * inv_l, v[e + 2] * inv_l, v[e + 3] * inv_l);
+            }
+          }
+        }
+      }
+    } else if (MODE == DENSE_DSCALE) {
+      // -sum_e dO_e (W_e - (m/l) O_e) / l for this row, this block of value columns
+      const float l = __ldg(P.rowsum + ((int64_t)sample * P.H + h_fixed) * P.N + (own_ok ? own : 0));
+      const float ratio = msum / lsum;  // m/l (lsum == l up to rounding)
+      float dot = 0.f;
+      for (int c0 = 0; c0 < NV; c0 += 32) {
+        float o[32], w[32];
+        tmem_ld32(lane_addr + c0, o);
+        tmem_ld32(lane_addr + NV + c0, w);
+        if (own_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const int n = n0 + c0 + e;
+            if (n < P.width) {
+              const int b = P.mesh_batched ? sample : n / P.D;
+              const int d = P.mesh_batched ? n : n - b * P.D;
+              const float4 g = __ldg(reinterpret_cast<const float4*>(P.d_out + ((int64_t)b * P.N + own) * P.ld_out + P.col_off +
+                                                                    (int64_t)h_fixed * P.D + d));
+              dot = fmaf(g.x, w[e] - ratio * o[e], dot);
+              dot = fmaf(g.y, w[e + 1] - ratio * o[e + 1], dot);
+              dot = fmaf(g.z, w[e + 2] - ratio * o[e + 2], dot);
+              dot = fmaf(g.w, w[e + 3] - ratio * o[e + 3], dot);
+            }
+          }
+        }
+      }
+      float v = own_ok ? -dot / l : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) red[warp] = v;
+      asm volatile("bar.sync 1, 128;");  // generator warps only
+      if (tid == 0) atomicAdd(P.d_scale + h_fixed, red[0] + red[1] + red[2] + red[3]);
+    } else {
+      // dU[b, j, :] (+ concat pass-through)
+      for (int c0 = 0; c0 < NV; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_addr + c0, v);
+        if (own_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const int n = n0 + c0 + e;
+            if (n < P.width) {
+              const int b = P.mesh_batched ? sample : n / P.D;
+              const int d = P.mesh_batched ? n : n - b * P.D;
+              float4 acc = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              if (P.add_concat) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(P.d_out + ((int64_t)b * P.N + own) * P.ld_out + d));
+                acc.x += g.x;
+                acc.y += g.y;
+                acc.z += g.z;
+                acc.w += g.w;
+              }
+              *reinterpret_cast<float4*>(P.d_values + ((int64_t)b * P.M + own) * P.D + d) = acc;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp < 8) {
+    // =========================== stagers: operand B ===========================
+    const int t = tid - DENSE_GEN_THREADS;
+    constexpr int CHUNKS_PER_ROW = NV / 4;                      // 16-byte chunks along N
+    constexpr int ROWS_PER_PASS = DENSE_STAGE_THREADS / CHUNKS_PER_ROW > 0 ? DENSE_STAGE_THREADS / CHUNKS_PER_ROW : 1;
+    constexpr int THREADS_PER_ROW = CHUNKS_PER_ROW < DENSE_STAGE_THREADS ? CHUNKS_PER_ROW : DENSE_STAGE_THREADS;
+    constexpr int CHUNKS_PER_THREAD = CHUNKS_PER_ROW / THREADS_PER_ROW;  // > 1 only when NV > 512 (never)
+    static_assert(CHUNKS_PER_THREAD == 1, "NV must be <= 512");
+    const int nc = t % THREADS_PER_ROW;
+    const int krow0 = t / THREADS_PER_ROW;
+    const int n = n0 + nc * 4;
+    const bool n_ok = n < P.width;
+    const int b = P.mesh_batched ? sample : (n_ok ? n / P.D : 0);
+    const int d = P.mesh_batched ? n : n - b * P.D;
+    const float* col_base = P.b_src + P.b_off + (int64_t)b * P.b_bstride + (n_ok ? d : 0);
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % DENSE_STAGES;
+      const uint32_t use = kb / DENSE_STAGES;
+      const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : 0;
+      const int k0 = (kb % kb_per_head) * DENSE_KB;
+      // issue the global loads before waiting for the stage to drain
+      float4 v[DENSE_KB / ROWS_PER_PASS];
+#pragma unroll
+      for (int it = 0; it < DENSE_KB / ROWS_PER_PASS; ++it) {
+        const int k = k0 + krow0 + it * ROWS_PER_PASS;
+        v[it] = (n_ok && k < P.n_red) ? __ldg(reinterpret_cast<const float4*>(col_base + (int64_t)k * P.b_kstride + (int64_t)h * P.b_hstride))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(&empty_bar[s], (use & 1) ^ 1);
+      unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES + L::A_TILES * L::A_BYTES;
+#pragma unroll
+      for (int it = 0; it < DENSE_KB / ROWS_PER_PASS; ++it) {
+        const int kk = krow0 + it * ROWS_PER_PASS;
+        const float4 hi = make_float4(tf32_hi(v[it].x), tf32_hi(v[it].y), tf32_hi(v[it].z), tf32_hi(v[it].w));
+        const float4 lo = make_float4(v[it].x - hi.x, v[it].y - hi.y, v[it].z - hi.z, v[it].w - hi.w);
+        const uint32_t off = b_chunk_offset(kk, nc);
+        *reinterpret_cast<float4*>(stage + off) = hi;
+        *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = lo;
+      }
+      fence_async_shared();
+      mbar_arrive(&full_bar[s]);
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t IDESC = umma_idesc_tf32(NV);
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % DENSE_STAGES;
+      const uint32_t use = kb / DENSE_STAGES;
+      mbar_wait(&full_bar[s], use & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_base = tiles + s * L::STAGE_BYTES;
+        const uint32_t b_base = a_base + L::A_TILES * L::A_BYTES;
+#pragma unroll
+        for (int kg = 0; kg < DENSE_KB / 8; ++kg) {
+          const uint32_t acc = (kb > 0 || kg > 0) ? 1u : 0u;
+          const uint64_t a_hi = umma_desc(a_base + kg * 32, 16, 1024);
+          const uint64_t a_lo = umma_desc(a_base + L::A_BYTES + kg * 32, 16, 1024);
+          const uint64_t b_hi = umma_desc(b_base + kg * 1024, 4096, 1024);
+          const uint64_t b_lo = umma_desc(b_base + L::B_BYTES + kg * 1024, 4096, 1024);
+          umma_tf32(tmem_base, a_hi, b_hi, IDESC, acc);
+          umma_tf32(tmem_base, a_lo, b_hi, IDESC, 1u);
+          umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
+          if (MODE == DENSE_DSCALE) {
+            const uint64_t ad_hi = umma_desc(a_base + 2 * L::A_BYTES + kg * 32, 16, 1024);
+            const uint64_t ad_lo = umma_desc(a_base + 3 * L::A_BYTES + kg * 32, 16, 1024);
+            umma_tf32(tmem_base + NV, ad_hi, b_hi, IDESC, acc);
+            umma_tf32(tmem_base + NV, ad_lo, b_hi, IDESC, 1u);
+            umma_tf32(tmem_base + NV, ad_hi, b_lo, IDESC, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // the stage may be overwritten once these MMAs have read it
+        if (kb == n_kb - 1) umma_commit(&done_bar);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace pit

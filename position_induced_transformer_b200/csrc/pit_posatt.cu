@@ -6,10 +6,12 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <type_traits>
 
+#include "dense_attention.cuh"
 #include "tall_attention.cuh"
 #include "wide_attention.cuh"
 #include "local_attention.cuh"
@@ -408,6 +410,76 @@ cudaError_t wide_dscale(int geo, const WidePlan& w, const pit::WideParams& P, cu
   });
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// dense (global) stages on tcgen05: eligibility, tile width, dispatch
+// ---------------------------------------------------------------------------------------------
+bool dense_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PIT_DENSE_TCGEN05");  // debugging switch: "0" keeps global stages on the SIMT kernels
+    cached = (e && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+bool dense_eligible(const pit_problem_t* p, const pit_rowstat_t* st) {
+  return dense_enabled() && !st->masked && p->dim % 4 == 0;
+}
+
+pit::DenseParams dense_params(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                              const float* scale, const pit_rowstat_t* st, int mode) {
+  pit::DenseParams P{};
+  const bool dv = mode == pit::DENSE_DVALUES;
+  P.mesh_own = dv ? mesh_in : mesh_out;
+  P.mesh_red = dv ? mesh_out : mesh_in;
+  P.period = p->variant == PIT_EUCLID ? nullptr : period;
+  P.scale = scale;
+  P.v_min = st->v_min;
+  P.n_own = dv ? p->n_in : p->n_out;
+  P.n_red = dv ? p->n_out : p->n_in;
+  P.N = p->n_out;
+  P.M = p->n_in;
+  P.B = p->batch;
+  P.H = p->n_head;
+  P.D = p->dim;
+  P.sd = p->space_dim;
+  P.mesh_batched = p->mesh_batched;
+  P.width = p->mesh_batched ? p->dim : p->batch * p->dim;
+  return P;
+}
+
+template <int GEO, int MODE, int NV>
+cudaError_t dense_launch_one(const pit::DenseParams& P, dim3 grid, cudaStream_t st) {
+  auto kernel = pit::dense_attention_kernel<GEO, MODE, NV>;
+  constexpr int smem = pit::DenseSmem<MODE, NV>::TOTAL;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<grid, pit::DENSE_THREADS, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t dense_launch(int geo, const pit_problem_t* p, const pit::DenseParams& P, cudaStream_t st) {
+  const int row_tiles = (P.n_own + pit::DENSE_ROWS - 1) / pit::DENSE_ROWS;
+  const int z = MODE == pit::DENSE_DVALUES ? (p->mesh_batched ? p->batch : 1) : p->n_head * (p->mesh_batched ? p->batch : 1);
+  // widest tile that still gives the GPU enough CTAs; the scale-gradient mode holds two accumulators (max 128 columns each)
+  int nv = MODE == pit::DENSE_DSCALE ? 128 : 256;
+  while (nv > 64 && ((int64_t)row_tiles * z * ((P.width + nv - 1) / nv) < sm_count() || nv / 2 >= P.width)) nv /= 2;
+  const dim3 grid(row_tiles, (P.width + nv - 1) / nv, z);
+  auto pick = [&](auto g) -> cudaError_t {
+    constexpr int G = decltype(g)::value;
+    if (nv == 64) return dense_launch_one<G, MODE, 64>(P, grid, st);
+    if (nv == 128) return dense_launch_one<G, MODE, 128>(P, grid, st);
+    if constexpr (MODE != pit::DENSE_DSCALE) return dense_launch_one<G, MODE, 256>(P, grid, st);
+    return cudaErrorInvalidValue;
+  };
+  if (geo == pit::GEO_EUCLID1) return pick(Int<pit::GEO_EUCLID1>{});
+  if (geo == pit::GEO_EUCLID2) return pick(Int<pit::GEO_EUCLID2>{});
+  if (geo == pit::GEO_PERIODIC1) return pick(Int<pit::GEO_PERIODIC1>{});
+  return pick(Int<pit::GEO_PERIODIC2>{});
+}
+
 // Sum of the per-row scale-gradient terms of one head (generic path): d_scale[h] = sum_rows rows[row*H + h].
 __global__ void reduce_scale_rows_kernel(const float* __restrict__ rows, int64_t n_rows, int H, float* __restrict__ d_scale) {
   __shared__ float red[32];
@@ -515,6 +587,19 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     PIT_CUDA(cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(float), values, (size_t)p->dim * sizeof(float),
                                (size_t)p->dim * sizeof(float), (size_t)p->batch * p->n_in, cudaMemcpyDeviceToDevice, st));
   }
+  if (dense_eligible(p, stat)) {
+    pit::DenseParams Dn = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_FWD);
+    Dn.b_src = values;
+    Dn.b_kstride = p->dim;
+    Dn.b_bstride = (int64_t)p->n_in * p->dim;
+    Dn.out = out;
+    Dn.ld_out = ld_out;
+    Dn.col_off = col_off;
+    Dn.rowsum_out = rowsum;
+    PIT_CUDA(dense_launch<pit::DENSE_FWD>(geo_of(p), p, Dn, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PIT_OK;
+  }
   const TallPlan plan = plan_tall_fwd(p);
   if (plan.ok) {
     pit::TallParams C = tall_params(p, plan, mesh_out, mesh_in, period, values, scale, stat);
@@ -590,7 +675,41 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   // masked cross stage, the value gradient too.  A dense self stage keeps the value gradient on the
   // column-owner kernel below (every column is touched by every row, slots would not help).
   bool values_done = d_values == nullptr, scale_done = d_scale == nullptr;
-  {
+  if (dense_eligible(p, stat)) {
+    if (d_scale) {
+      pit::DenseParams Dn = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_DSCALE);
+      Dn.rowsum = rowsum;
+      Dn.b_src = values;
+      Dn.b_kstride = p->dim;
+      Dn.b_bstride = (int64_t)p->n_in * p->dim;
+      Dn.d_out = d_out;
+      Dn.ld_out = ld_out;
+      Dn.col_off = col_off;
+      Dn.d_scale = d_scale;
+      PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
+      PIT_CUDA(dense_launch<pit::DENSE_DSCALE>(geo, p, Dn, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      scale_done = true;
+    }
+    if (d_values) {
+      pit::DenseParams Dn = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_DVALUES);
+      Dn.rowsum = rowsum;
+      Dn.b_src = d_out;
+      Dn.b_kstride = ld_out;
+      Dn.b_bstride = (int64_t)p->n_out * ld_out;
+      Dn.b_hstride = p->dim;
+      Dn.b_off = col_off;
+      Dn.d_out = d_out;
+      Dn.ld_out = ld_out;
+      Dn.col_off = col_off;
+      Dn.d_values = d_values;
+      Dn.add_concat = accumulate_concat;
+      PIT_CUDA(dense_launch<pit::DENSE_DVALUES>(geo, p, Dn, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      values_done = true;
+    }
+  }
+  if (!(values_done && scale_done)) {
     const bool fuse_values = d_values && stat->masked && !accumulate_concat;
     const TallPlan plan = plan_tall_bwd(p, fuse_values);
     if (plan.ok && (d_scale || fuse_values)) {
