@@ -10,7 +10,9 @@
 //              TF32 high part and an fp32 residual, and writes both as UMMA operand A (K-major,
 //              128-byte swizzle) into shared memory; it also keeps the fp32 row sum.
 //   warps 4-7  "stagers": stream the [32 x NV] value block from global memory with 128-bit loads,
-//              split hi/lo the same way, and lay it out as UMMA operand B (MN-major, 128-byte swizzle).
+//              transpose 4x4 sub-blocks in registers, split hi/lo the same way, and lay the block out as
+//              UMMA operand B (K-major, 128-byte swizzle; an MN-major tf32 B operand reads back as zeros
+//              on sm_100a -- scripts/probe/umma_probe.cu -- hence the in-register transpose).
 //   warp 8     one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=NV, K=8): hi*hi + lo*hi + hi*lo,
 //              i.e. 3xTF32 with fp32 accumulation in TMEM (error ~2^-21, inside the 1e-5 parity budget),
 //              then tcgen05.commit's the stage back to the producers through an mbarrier.
@@ -138,8 +140,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor), SWIZZLE_128B, version 1.
-//   K-major  operand (A): rows of 128 bytes (32 tf32 along K), 8-row groups 1024 bytes apart (SBO); LBO unused (1).
-//   MN-major operand (B): atoms of 8 K-rows x 128 bytes (32 tf32 along N); next atom along N at LBO, next 8 K-rows at SBO.
+//   K-major operand (A and B): rows of 128 bytes (32 tf32 along K), 8-row groups 1024 bytes apart (SBO); LBO unused (1).
+//   One MMA consumes K = 8 tf32 = 32 bytes of every row: the k-th step starts 32*k bytes into the tile.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -149,20 +151,22 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor (InstrDescriptor): D=F32, A=B=TF32, A K-major, B MN-major, M=128, N=NV.
+// Instruction descriptor (InstrDescriptor): D=F32, A=B=TF32, both K-major, M=128, N=NV.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(DENSE_ROWS >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(DENSE_ROWS >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// High part of the 3xTF32 split: x rounded to nearest at tf32 precision (10 explicit mantissa bits), so that the
+// residual x - hi fits the next tf32 with half the truncation error of a plain mask.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // Byte offset of the 16-byte chunk (row r, chunk c of 8) inside a K-major 128B-swizzled tile of 128 rows.
 __device__ __forceinline__ uint32_t a_chunk_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
-// Byte offset of the 16-byte chunk (k row of 32, n chunk nc of NV/4) inside an MN-major 128B-swizzled [32 x NV] tile:
-// atom index = (nc / 8) * 4 + k / 8, so LBO (next 32 columns) = 4096 bytes and SBO (next 8 k rows) = 1024 bytes.
-__device__ __forceinline__ uint32_t b_chunk_offset(int k, int nc) {
-  return (uint32_t)((((nc >> 3) << 2) + (k >> 3)) * 1024 + (k & 7) * 128 + (((nc & 7) ^ (k & 7)) << 4));
-}
+// Operand B uses the same K-major layout with the value column n as the tile row:
+// 16-byte chunk holding k = 4*kq .. 4*kq+3 of column n.
+__device__ __forceinline__ uint32_t b_chunk_offset(int n, int kq) { return a_chunk_offset(n, kq); }
+
+__device__ __forceinline__ float pick4(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
 
 template <int MODE, int NV>
 struct DenseSmem {
@@ -374,15 +378,19 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     tc_fence_before();
   } else if (warp < 8) {
     // =========================== stagers: operand B ===========================
+    // A thread owns 4(k) x 4(n) sub-blocks: four 128-bit loads along n (coalesced across the warp), a register
+    // transpose, four 128-bit stores along k.  Which of its four columns a lane stores at each step is rotated by
+    // lane/2 so that a quarter warp always hits eight different 16-byte bank groups of the swizzled tile.
     const int t = tid - DENSE_GEN_THREADS;
-    constexpr int CHUNKS_PER_ROW = NV / 4;                      // 16-byte chunks along N
-    constexpr int ROWS_PER_PASS = DENSE_STAGE_THREADS / CHUNKS_PER_ROW > 0 ? DENSE_STAGE_THREADS / CHUNKS_PER_ROW : 1;
-    constexpr int THREADS_PER_ROW = CHUNKS_PER_ROW < DENSE_STAGE_THREADS ? CHUNKS_PER_ROW : DENSE_STAGE_THREADS;
-    constexpr int CHUNKS_PER_THREAD = CHUNKS_PER_ROW / THREADS_PER_ROW;  // > 1 only when NV > 512 (never)
-    static_assert(CHUNKS_PER_THREAD == 1, "NV must be <= 512");
-    const int nc = t % THREADS_PER_ROW;
-    const int krow0 = t / THREADS_PER_ROW;
-    const int n = n0 + nc * 4;
+    constexpr int NQ = NV / 4;                                   // column quads per tile
+    constexpr int BLOCKS = (DENSE_KB / 4) * NQ;                  // 4x4 sub-blocks per K block
+    constexpr int PER_THREAD = BLOCKS / DENSE_STAGE_THREADS;     // 1 (NV=64), 2 (NV=128), 4 (NV=256)
+    static_assert(BLOCKS % DENSE_STAGE_THREADS == 0, "NV must be a multiple of 64");
+    constexpr int T_PER_KQ = NQ < DENSE_STAGE_THREADS ? NQ : DENSE_STAGE_THREADS;  // threads that share one k-quad
+    const int nq = t % T_PER_KQ;
+    const int kq0 = t / T_PER_KQ;
+    constexpr int KQ_STEP = DENSE_STAGE_THREADS / T_PER_KQ;
+    const int n = n0 + nq * 4;
     const bool n_ok = n < P.width;
     const int b = P.mesh_batched ? sample : (n_ok ? n / P.D : 0);
     const int d = P.mesh_batched ? n : n - b * P.D;
@@ -393,23 +401,33 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
       const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : 0;
       const int k0 = (kb % kb_per_head) * DENSE_KB;
       // issue the global loads before waiting for the stage to drain
-      float4 v[DENSE_KB / ROWS_PER_PASS];
+      float4 v[PER_THREAD][4];
 #pragma unroll
-      for (int it = 0; it < DENSE_KB / ROWS_PER_PASS; ++it) {
-        const int k = k0 + krow0 + it * ROWS_PER_PASS;
-        v[it] = (n_ok && k < P.n_red) ? __ldg(reinterpret_cast<const float4*>(col_base + (int64_t)k * P.b_kstride + (int64_t)h * P.b_hstride))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < PER_THREAD; ++it) {
+        const int kq = kq0 + it * KQ_STEP;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + kq * 4 + j;
+          v[it][j] = (n_ok && k < P.n_red)
+                         ? __ldg(reinterpret_cast<const float4*>(col_base + (int64_t)k * P.b_kstride + (int64_t)h * P.b_hstride))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       mbar_wait(&empty_bar[s], (use & 1) ^ 1);
       unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES + L::A_TILES * L::A_BYTES;
 #pragma unroll
-      for (int it = 0; it < DENSE_KB / ROWS_PER_PASS; ++it) {
-        const int kk = krow0 + it * ROWS_PER_PASS;
-        const float4 hi = make_float4(tf32_hi(v[it].x), tf32_hi(v[it].y), tf32_hi(v[it].z), tf32_hi(v[it].w));
-        const float4 lo = make_float4(v[it].x - hi.x, v[it].y - hi.y, v[it].z - hi.z, v[it].w - hi.w);
-        const uint32_t off = b_chunk_offset(kk, nc);
-        *reinterpret_cast<float4*>(stage + off) = hi;
-        *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = lo;
+      for (int it = 0; it < PER_THREAD; ++it) {
+        const int kq = kq0 + it * KQ_STEP;
+#pragma unroll
+        for (int step = 0; step < 4; ++step) {
+          const int e = (step + (lane >> 1)) & 3;  // column of the sub-block stored at this step
+          const float x0 = pick4(v[it][0], e), x1 = pick4(v[it][1], e), x2 = pick4(v[it][2], e), x3 = pick4(v[it][3], e);
+          const float4 hi = make_float4(tf32_hi(x0), tf32_hi(x1), tf32_hi(x2), tf32_hi(x3));
+          const float4 lo = make_float4(x0 - hi.x, x1 - hi.y, x2 - hi.z, x3 - hi.w);
+          const uint32_t off = b_chunk_offset(nq * 4 + e, kq);
+          *reinterpret_cast<float4*>(stage + off) = hi;
+          *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = lo;
+        }
       }
       fence_async_shared();
       mbar_arrive(&full_bar[s]);
@@ -430,8 +448,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
           const uint32_t acc = (kb > 0 || kg > 0) ? 1u : 0u;
           const uint64_t a_hi = umma_desc(a_base + kg * 32, 16, 1024);
           const uint64_t a_lo = umma_desc(a_base + L::A_BYTES + kg * 32, 16, 1024);
-          const uint64_t b_hi = umma_desc(b_base + kg * 1024, 4096, 1024);
-          const uint64_t b_lo = umma_desc(b_base + L::B_BYTES + kg * 1024, 4096, 1024);
+          const uint64_t b_hi = umma_desc(b_base + kg * 32, 16, 1024);
+          const uint64_t b_lo = umma_desc(b_base + L::B_BYTES + kg * 32, 16, 1024);
           umma_tf32(tmem_base, a_hi, b_hi, IDESC, acc);
           umma_tf32(tmem_base, a_lo, b_hi, IDESC, 1u);
           umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
