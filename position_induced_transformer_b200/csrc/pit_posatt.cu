@@ -225,7 +225,7 @@ TallPlan plan_tall_bwd(const pit_problem_t* p, bool with_values) {
   c.n_slots = 0;
   if (with_values) {
     const int per_slot = c.lanes4 * 16;
-    c.n_slots = 48 * 1024 / per_slot;
+    c.n_slots = 32 * 1024 / per_slot;
     if (c.n_slots > 64) c.n_slots = 64;
     if (c.n_slots > p->n_in) c.n_slots = p->n_in;
     if (c.n_slots < 4) return c;

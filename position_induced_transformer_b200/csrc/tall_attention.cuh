@@ -56,9 +56,12 @@ struct TallParams {
 };
 
 // Scan one row.  `post[h]` multiplies the stored weight (1 forward, 1/l backward).  Returns the entry count.
-template <int GEO, int CPL, int NH>
+// `vcap` is a head-independent pre-filter in d2 space: a kept column satisfies fl(d2*s) <= T <= fl(v_hi*s), and
+// rounding is monotone, so d2 > v_hi*(1+2^-20) can never be kept; whole 32-column groups without a candidate
+// skip the per-head work.  The exact per-head test still decides.
+template <int GEO, int CPL, int NH, bool BACKWARD>
 __device__ __forceinline__ int tall_scan_row(const Point<GEO>& o, const Point<GEO> (&col)[CPL], int M, int lane, float period,
-                                             const float (&s)[NH], const float (&top)[NH], const float (&cut)[NH],
+                                             float vcap, const float (&s)[NH], const float (&top)[NH], const float (&cut)[NH],
                                              const float (&post)[NH], float4* seg, uint8_t* touched, float (&psum)[NH],
                                              float (&pdsum)[NH]) {
   int n = 0;
@@ -67,25 +70,29 @@ __device__ __forceinline__ int tall_scan_row(const Point<GEO>& o, const Point<GE
   for (int c = 0; c < CPL; ++c) {
     const int j = c * 32 + lane;
     const float d2 = dist2<GEO>(o, col[c], period);
+    const bool cand = (j < M) && (d2 <= vcap);
+    if (!__any_sync(FULL, cand)) continue;
     float p[NH];
     bool any = false;
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
       p[h] = 0.f;
-      if (j < M) {
+      if (cand) {
         const float sc = __fmul_rn(d2, s[h]);
-        if (sc <= cut[h]) p[h] = expf(__fsub_rn(top[h], sc));
+        if (sc <= cut[h]) p[h] = __expf(__fsub_rn(top[h], sc));
       }
       psum[h] += p[h];
-      p[h] *= post[h];
-      pdsum[h] = fmaf(p[h], d2, pdsum[h]);
+      if (BACKWARD) {
+        p[h] *= post[h];
+        pdsum[h] = fmaf(p[h], d2, pdsum[h]);
+      }
       any = any || (p[h] > 0.f);
     }
     const unsigned m = __ballot_sync(FULL, any);
     if (any) {
       const int pos = n + __popc(m & lt);
       seg[pos] = make_float4(__int_as_float(j), d2, p[0], NH > 1 ? p[NH - 1] : 0.f);
-      if (touched) touched[j] = 1;
+      if (BACKWARD && touched) touched[j] = 1;
     }
     n += __popc(m);
   }
@@ -141,7 +148,8 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_fwd_kernel(const TallParams
       psum[h] = 0.f;
       pdsum[h] = 0.f;
     }
-    const int n = tall_scan_row<GEO, CPL, NH>(o, col, P.M, lane, period, s, top, cut, post, seg, nullptr, psum, pdsum);
+    const float vcap = P.masked ? vhi * 1.000001f : INFINITY;
+    const int n = tall_scan_row<GEO, CPL, NH, false>(o, col, P.M, lane, period, vcap, s, top, cut, post, seg, nullptr, psum, pdsum);
     __syncwarp();
     float inv_l[NH];
 #pragma unroll
@@ -343,8 +351,9 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_bwd_kernel(const TallParams
         psum[h] = 0.f;
         pdsum[h] = 0.f;
       }
-      const int n = tall_scan_row<GEO, CPL, NH>(o, col, P.M, lane, period, s, top, cut, post, S.seg + (size_t)warp * SEG,
-                                                WITH_VALUES ? S.touched : nullptr, psum, pdsum);
+      const float vcap = P.masked ? vhi * 1.000001f : INFINITY;
+      const int n = tall_scan_row<GEO, CPL, NH, true>(o, col, P.M, lane, period, vcap, s, top, cut, post, S.seg + (size_t)warp * SEG,
+                                                      WITH_VALUES ? S.touched : nullptr, psum, pdsum);
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         const float m = warp_sum(pdsum[h]);
@@ -395,15 +404,17 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_bwd_kernel(const TallParams
       const int r = r0 + w;
       const int n = S.cnt[w];
       const float4* seg = S.seg + (size_t)w * SEG;
-      float4 g[NH][L4], acc_o[NH][L4], acc_w[NH][L4];
+      // d scale: -sum_e dO_e (W_e - m O_e) = -sum_e dO_e Z_e with Z = sum_j P^_j (d2_j - m) U_j  (one accumulator per head)
+      float4 g[NH][L4], acc_z[NH][L4];
+      float mrow[NH];
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
+        mrow[h] = S.rowm[w * 2 + h];
 #pragma unroll
         for (int k = 0; k < L4; ++k) {
           g[h][k] = ok[k] ? __ldg(reinterpret_cast<const float4*>(P.d_out + g_off[k] + (int64_t)r * P.ld_out + (int64_t)h * P.D))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
-          acc_o[h][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          acc_w[h][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          acc_z[h][k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       for (int e0 = 0; e0 < n; e0 += G) {
@@ -428,18 +439,13 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_bwd_kernel(const TallParams
           if (want_scale) {
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
-              const float pw = h == 0 ? ent[t].z : ent[t].w;
-              const float pd = pw * d2;
+              const float pz = (h == 0 ? ent[t].z : ent[t].w) * (d2 - mrow[h]);
 #pragma unroll
               for (int k = 0; k < L4; ++k) {
-                acc_o[h][k].x = fmaf(pw, u[t][k].x, acc_o[h][k].x);
-                acc_o[h][k].y = fmaf(pw, u[t][k].y, acc_o[h][k].y);
-                acc_o[h][k].z = fmaf(pw, u[t][k].z, acc_o[h][k].z);
-                acc_o[h][k].w = fmaf(pw, u[t][k].w, acc_o[h][k].w);
-                acc_w[h][k].x = fmaf(pd, u[t][k].x, acc_w[h][k].x);
-                acc_w[h][k].y = fmaf(pd, u[t][k].y, acc_w[h][k].y);
-                acc_w[h][k].z = fmaf(pd, u[t][k].z, acc_w[h][k].z);
-                acc_w[h][k].w = fmaf(pd, u[t][k].w, acc_w[h][k].w);
+                acc_z[h][k].x = fmaf(pz, u[t][k].x, acc_z[h][k].x);
+                acc_z[h][k].y = fmaf(pz, u[t][k].y, acc_z[h][k].y);
+                acc_z[h][k].z = fmaf(pz, u[t][k].z, acc_z[h][k].z);
+                acc_z[h][k].w = fmaf(pz, u[t][k].w, acc_z[h][k].w);
               }
             }
           }
@@ -473,14 +479,13 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_bwd_kernel(const TallParams
       if (want_scale) {
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
-          const float m = S.rowm[w * 2 + h];
           float dot = 0.f;
 #pragma unroll
           for (int k = 0; k < L4; ++k) {
-            dot = fmaf(g[h][k].x, acc_w[h][k].x - m * acc_o[h][k].x, dot);
-            dot = fmaf(g[h][k].y, acc_w[h][k].y - m * acc_o[h][k].y, dot);
-            dot = fmaf(g[h][k].z, acc_w[h][k].z - m * acc_o[h][k].z, dot);
-            dot = fmaf(g[h][k].w, acc_w[h][k].w - m * acc_o[h][k].w, dot);
+            dot = fmaf(g[h][k].x, acc_z[h][k].x, dot);
+            dot = fmaf(g[h][k].y, acc_z[h][k].y, dot);
+            dot = fmaf(g[h][k].z, acc_z[h][k].z, dot);
+            dot = fmaf(g[h][k].w, acc_z[h][k].w, dot);
           }
           ds_head[h] += dot;
         }
