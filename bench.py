@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-batch", type=int, default=0, help="samples per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--precision", default="high", choices=["high", "highest"],
                     help="torch matmul precision for the MLP Linears (reference pit.py:2 sets 'high')")
     return ap.parse_args()
@@ -199,6 +200,7 @@ def default_batch(name: str) -> int:
 
 def bench_config(args, batch):
     return {"workload": args.workload, "per_gpu_batch": batch, "global_batch": batch * args.gpus, "step": STEP_DESC,
+            "launch": "eager" if getattr(args, "no_graph", False) else "cuda_graph_replay",
             "parallelism": f"dp{args.gpus}", "mlp_matmul_precision": args.precision,
             "l2": "per-step working set (activations of the decoder stage) exceeds the 126 MB L2 and input batches rotate over 4 buffers; no explicit flush"}
 
@@ -210,6 +212,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from position_induced_transformer_b200 import _cabi, posatt, workloads
     from position_induced_transformer_b200.data_parallel import FlatGradients
+    from position_induced_transformer_b200.graphed import GraphedTrainStep
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     dev = torch.device("cuda", local_rank)
@@ -218,8 +221,8 @@ def run_ours(args, rank, world, local_rank):
     batch = args.batch or default_batch(args.workload)
     w = workloads.WORKLOADS[args.workload](batch).to(dev)
     model = w.model
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    flat = FlatGradients(model.parameters(), world)
+    use_graph = not args.no_graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph)
     gen = torch.Generator().manual_seed(1234 + rank)
     n_buf = 4
     host = [w.make_batch(gen, batch) for _ in range(n_buf)]
@@ -227,13 +230,22 @@ def run_ours(args, rank, world, local_rank):
     resident = [(tuple(x.to(dev) for x in ins), tgt.to(dev)) for ins, tgt in host]
     h2d_bytes = sum(x.numel() * x.element_size() for x in host[0][0]) + host[0][1].numel() * 4
 
-    def step(ins, target):
-        flat.zero()
-        loss = w.loss(target, workloads.run_model(w, ins))
-        loss.backward()
-        flat.all_reduce()
-        opt.step()
-        return loss
+    def forward_loss(ins, target):
+        return w.loss(target, workloads.run_model(w, ins))
+
+    if use_graph:
+        # the whole step (zero grads, forward, loss, backward, all-reduce, Adam) is captured once and replayed
+        step = GraphedTrainStep(list(model.parameters()), forward_loss, opt, resident[0][0], resident[0][1], world)
+    else:
+        flat = FlatGradients(model.parameters(), world)
+
+        def step(ins, target):
+            flat.zero()
+            loss = forward_loss(ins, target)
+            loss.backward()
+            flat.all_reduce()
+            opt.step()
+            return loss
 
     def barrier():
         if world > 1:
@@ -244,9 +256,6 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup):
         step(*resident[i % n_buf])
     barrier()
-    launches0 = _cabi.launch_count()
-    timer = posatt.KernelTimer()
-    posatt.set_kernel_timer(timer)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -257,9 +266,25 @@ def run_ours(args, rank, world, local_rank):
     end.record()
     barrier()
     clock_info = clocks.stop() if rank == 0 else None
-    posatt.set_kernel_timer(None)
     ms = start.elapsed_time(end)
-    launches = _cabi.launch_count() - launches0
+
+    # ---- per-kernel timing: the same step launched eagerly with CUDA events around every C-ABI call ----
+    eager = step._eager if use_graph else (lambda: step(*resident[0]))
+    eager()
+    barrier()
+    launches0 = _cabi.launch_count()
+    timer = posatt.KernelTimer()
+    posatt.set_kernel_timer(timer)
+    k_steps = min(args.steps, 5)
+    k_start, k_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_start.record()
+    for _ in range(k_steps):
+        eager()
+    k_end.record()
+    barrier()
+    posatt.set_kernel_timer(None)
+    eager_ms = k_start.elapsed_time(k_end) / k_steps
+    launches = (_cabi.launch_count() - launches0) // k_steps * args.steps   # the graph replays exactly these launches
     kernels = timer.summary()
 
     # ---- end to end: host inputs, H2D every step, loss read back every step ----
@@ -293,14 +318,14 @@ def run_ours(args, rank, world, local_rank):
         if top is not None:
             q = algorithmic_bytes(top)
             ach = q / (kernels[top]["ms_avg"] * 1e-3) / 1e9
-            share = kernels[top]["ms_total"] / ms
+            share = kernels[top]["ms_avg"] * kernels[top]["calls"] / k_steps / (ms / args.steps)
             roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                         "kernel": {"call": top[0], "variant": top[1], "mesh_batched": bool(top[2]), "B": top[3], "H": top[4],
                                    "N": top[5], "M": top[6], "D": top[7]},
                         "algorithmic_bytes_per_launch": q, "avg_launch_ms": kernels[top]["ms_avg"],
                         "share_of_step": share, "peak_source": peak_src}
     kernel_table = sorted(({"call": k[0], "N": k[5], "M": k[6], "D": k[7], "concat": bool(k[9]), "ms_avg": v["ms_avg"],
-                            "calls_per_step": v["calls"] / args.steps, "share_of_step": v["ms_total"] / ms,
+                            "calls_per_step": v["calls"] / k_steps, "share_of_step": v["ms_total"] / k_steps / (ms / args.steps),
                             "GBps_algorithmic": algorithmic_bytes(k) / (v["ms_avg"] * 1e-3) / 1e9} for k, v in kernels.items()),
                           key=lambda r: -r["share_of_step"])
 
@@ -318,7 +343,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic", "config": bench_config(args, batch),
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info, "kernels": kernel_table[:8],
+        "gpu_launches": launches, "eager_ms_per_step": eager_ms, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info, "kernels": kernel_table[:8],
     }
     print(json.dumps(line), flush=True)
 

@@ -194,7 +194,7 @@ def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
 def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, locality: float):
     """Contiguous meshes, the validated stage, the wrap period and the row statistics -- cached for shared meshes."""
     batched = mesh_in.dim() == 3
-    cacheable = mesh_cache.enabled and not batched and mesh_in.is_cuda and not torch.cuda.is_current_stream_capturing()
+    cacheable = mesh_cache.enabled and not batched and mesh_in.is_cuda
     key = mesh_cache.key(mesh_out, mesh_in, variant, locality) if cacheable else None
     hit = mesh_cache.get(key) if cacheable else None
     if hit is not None:
@@ -205,7 +205,8 @@ def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, localit
     with torch.cuda.device(st.device):
         period = wrap_period(mi, variant)
         stats = row_statistics(st, mo, mi, period, float(locality))
-    if cacheable:
+    # entries created while a CUDA graph is being captured would point into the graph's private pool: do not keep them
+    if cacheable and not torch.cuda.is_current_stream_capturing():
         mesh_cache.put(key, (mo, mi, period, stats), (mesh_out, mesh_in))
     return mo, mi, st, period, stats
 
