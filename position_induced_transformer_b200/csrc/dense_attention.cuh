@@ -9,10 +9,11 @@
 //              coordinates (exp2 with the row's known shift, so no online rescaling), splits each into a
 //              TF32 high part and an fp32 residual, and writes both as UMMA operand A (K-major,
 //              128-byte swizzle) into shared memory; it also keeps the fp32 row sum.
-//   warps 4-7  "stagers": stream the [32 x NV] value block from global memory with 128-bit loads,
-//              transpose 4x4 sub-blocks in registers, split hi/lo the same way, and lay the block out as
-//              UMMA operand B (K-major, 128-byte swizzle; an MN-major tf32 B operand reads back as zeros
-//              on sm_100a -- scripts/probe/umma_probe.cu -- hence the in-register transpose).
+//   warps 4-7  "stagers": stream the [32 x NV] value block from global memory with 128-bit loads, split
+//              hi/lo the same way, and store it as UMMA operand B in MN-major form.  For 32-bit operands the
+//              MN-major canonical layout is SWIZZLE_128B_BASE32B (atoms of 4 K-rows x 128 bytes, 32-byte chunks
+//              XOR-ed with the K row); with the plain SWIZZLE_128B descriptor a tf32 MN-major operand reads back
+//              as zeros (measured: scripts/probe/umma_probe.cu, modes 0/1 vs 5).  No transpose is needed.
 //   warp 8     one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=NV, K=8): hi*hi + lo*hi + hi*lo,
 //              i.e. 3xTF32 with fp32 accumulation in TMEM (error ~2^-21, inside the 1e-5 parity budget),
 //              then tcgen05.commit's the stage back to the producers through an mbarrier.
@@ -151,9 +152,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor (InstrDescriptor): D=F32, A=B=TF32, both K-major, M=128, N=NV.
+// Instruction descriptor (InstrDescriptor): D=F32, A=B=TF32, A K-major, B MN-major, M=128, N=NV.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(DENSE_ROWS >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(DENSE_ROWS >> 4) << 24);
 }
 
 // High part of the 3xTF32 split: x rounded to nearest at tf32 precision (10 explicit mantissa bits), so that the
@@ -162,11 +163,27 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__fl
 
 // Byte offset of the 16-byte chunk (row r, chunk c of 8) inside a K-major 128B-swizzled tile of 128 rows.
 __device__ __forceinline__ uint32_t a_chunk_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
-// Operand B uses the same K-major layout with the value column n as the tile row:
-// 16-byte chunk holding k = 4*kq .. 4*kq+3 of column n.
-__device__ __forceinline__ uint32_t b_chunk_offset(int n, int kq) { return a_chunk_offset(n, kq); }
+// Operand B, MN-major SWIZZLE_128B_BASE32B: atoms of 4 K-rows x 128 bytes (32 value columns); inside an atom the
+// 32-byte chunk index is XOR-ed with the K row.  Atoms of one 32-column group are contiguous along K (SBO = 512
+// bytes per 4 K-rows), column groups are DENSE_KB/4 atoms apart (LBO = 4096 bytes).  One MMA (K = 8) spans two atoms.
+constexpr uint32_t B_SBO = 512, B_LBO = (DENSE_KB / 4) * 512, B_KSTEP = 1024;
+// Byte offset of the 16-byte piece holding columns 4*n4 .. 4*n4+3 of K-row k.
+__device__ __forceinline__ uint32_t b_chunk_offset(int k, int n4) {
+  const int kr = k & 3;
+  return (uint32_t)((n4 >> 3) * B_LBO + (k >> 2) * B_SBO + kr * 128 + (((((n4 & 7) >> 1) ^ kr)) << 5) + (n4 & 1) * 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_b(uint32_t smem_addr) {
+  uint64_t d = umma_desc(smem_addr, B_LBO, B_SBO);
+  d &= ~((uint64_t)7 << 61);
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
 
-__device__ __forceinline__ float pick4(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int MODE, int NV>
 struct DenseSmem {
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
           other.y = q.y;
           const float d2 = (MODE == DENSE_DVALUES) ? dist2<GEO>(other, me, period) : dist2<GEO>(me, other, period);
           const float vm = (MODE == DENSE_DVALUES) ? q.z : own_vmin;
-          float p = exp2f((vm - d2) * sc2) * q.w;
+          float p = fast_exp2((vm - d2) * sc2) * q.w;
           if (!own_ok) p = 0.f;
           lsum += p;
           hi[e] = tf32_hi(p);
@@ -378,19 +395,17 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     tc_fence_before();
   } else if (warp < 8) {
     // =========================== stagers: operand B ===========================
-    // A thread owns 4(k) x 4(n) sub-blocks: four 128-bit loads along n (coalesced across the warp), a register
-    // transpose, four 128-bit stores along k.  Which of its four columns a lane stores at each step is rotated by
-    // lane/2 so that a quarter warp always hits eight different 16-byte bank groups of the swizzled tile.
+    // 128-bit loads along the value columns (coalesced), hi/lo split, 128-bit stores into the MN-major tile: a
+    // quarter warp writes the eight 16-byte pieces of one 128-byte atom row, so the stores are conflict-free.
     const int t = tid - DENSE_GEN_THREADS;
-    constexpr int NQ = NV / 4;                                   // column quads per tile
-    constexpr int BLOCKS = (DENSE_KB / 4) * NQ;                  // 4x4 sub-blocks per K block
-    constexpr int PER_THREAD = BLOCKS / DENSE_STAGE_THREADS;     // 1 (NV=64), 2 (NV=128), 4 (NV=256)
-    static_assert(BLOCKS % DENSE_STAGE_THREADS == 0, "NV must be a multiple of 64");
-    constexpr int T_PER_KQ = NQ < DENSE_STAGE_THREADS ? NQ : DENSE_STAGE_THREADS;  // threads that share one k-quad
-    const int nq = t % T_PER_KQ;
-    const int kq0 = t / T_PER_KQ;
-    constexpr int KQ_STEP = DENSE_STAGE_THREADS / T_PER_KQ;
-    const int n = n0 + nq * 4;
+    constexpr int N4 = NV / 4;                                               // 16-byte pieces per K-row
+    constexpr int T_PER_ROW = N4 < DENSE_STAGE_THREADS ? N4 : DENSE_STAGE_THREADS;
+    constexpr int ROWS_PER_PASS = DENSE_STAGE_THREADS / T_PER_ROW;
+    constexpr int PASSES = DENSE_KB / ROWS_PER_PASS;                         // 16 (NV=256), 8 (128), 4 (64)
+    static_assert(N4 <= DENSE_STAGE_THREADS, "NV must be <= 512");
+    const int n4 = t % T_PER_ROW;
+    const int krow0 = t / T_PER_ROW;
+    const int n = n0 + n4 * 4;
     const bool n_ok = n < P.width;
     const int b = P.mesh_batched ? sample : (n_ok ? n / P.D : 0);
     const int d = P.mesh_batched ? n : n - b * P.D;
@@ -401,33 +416,22 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
       const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : 0;
       const int k0 = (kb % kb_per_head) * DENSE_KB;
       // issue the global loads before waiting for the stage to drain
-      float4 v[PER_THREAD][4];
+      float4 v[PASSES];
 #pragma unroll
-      for (int it = 0; it < PER_THREAD; ++it) {
-        const int kq = kq0 + it * KQ_STEP;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = k0 + kq * 4 + j;
-          v[it][j] = (n_ok && k < P.n_red)
-                         ? __ldg(reinterpret_cast<const float4*>(col_base + (int64_t)k * P.b_kstride + (int64_t)h * P.b_hstride))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int it = 0; it < PASSES; ++it) {
+        const int k = k0 + krow0 + it * ROWS_PER_PASS;
+        v[it] = (n_ok && k < P.n_red) ? __ldg(reinterpret_cast<const float4*>(col_base + (int64_t)k * P.b_kstride + (int64_t)h * P.b_hstride))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait(&empty_bar[s], (use & 1) ^ 1);
       unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES + L::A_TILES * L::A_BYTES;
 #pragma unroll
-      for (int it = 0; it < PER_THREAD; ++it) {
-        const int kq = kq0 + it * KQ_STEP;
-#pragma unroll
-        for (int step = 0; step < 4; ++step) {
-          const int e = (step + (lane >> 1)) & 3;  // column of the sub-block stored at this step
-          const float x0 = pick4(v[it][0], e), x1 = pick4(v[it][1], e), x2 = pick4(v[it][2], e), x3 = pick4(v[it][3], e);
-          const float4 hi = make_float4(tf32_hi(x0), tf32_hi(x1), tf32_hi(x2), tf32_hi(x3));
-          const float4 lo = make_float4(x0 - hi.x, x1 - hi.y, x2 - hi.z, x3 - hi.w);
-          const uint32_t off = b_chunk_offset(nq * 4 + e, kq);
-          *reinterpret_cast<float4*>(stage + off) = hi;
-          *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = lo;
-        }
+      for (int it = 0; it < PASSES; ++it) {
+        const float4 hi = make_float4(tf32_hi(v[it].x), tf32_hi(v[it].y), tf32_hi(v[it].z), tf32_hi(v[it].w));
+        const float4 lo = make_float4(v[it].x - hi.x, v[it].y - hi.y, v[it].z - hi.z, v[it].w - hi.w);
+        const uint32_t off = b_chunk_offset(krow0 + it * ROWS_PER_PASS, n4);
+        *reinterpret_cast<float4*>(stage + off) = hi;
+        *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = lo;
       }
       fence_async_shared();
       mbar_arrive(&full_bar[s]);
@@ -448,8 +452,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
           const uint32_t acc = (kb > 0 || kg > 0) ? 1u : 0u;
           const uint64_t a_hi = umma_desc(a_base + kg * 32, 16, 1024);
           const uint64_t a_lo = umma_desc(a_base + L::A_BYTES + kg * 32, 16, 1024);
-          const uint64_t b_hi = umma_desc(b_base + kg * 32, 16, 1024);
-          const uint64_t b_lo = umma_desc(b_base + L::B_BYTES + kg * 32, 16, 1024);
+          const uint64_t b_hi = umma_desc_b(b_base + kg * B_KSTEP);
+          const uint64_t b_lo = umma_desc_b(b_base + L::B_BYTES + kg * B_KSTEP);
           umma_tf32(tmem_base, a_hi, b_hi, IDESC, acc);
           umma_tf32(tmem_base, a_lo, b_hi, IDESC, 1u);
           umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);

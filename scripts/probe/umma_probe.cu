@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(ProbeArgs P) {
     uint32_t off;
     if (P.mode == 0 || P.mode == 1) off = (uint32_t)((((n >> 5) << 2) + (k >> 3)) * 1024 + (k & 7) * 128 + ((((n >> 2) & 7) ^ (k & 7)) << 4)) + (n & 3) * 4;  // MN-major SW128 atoms
     else if (P.mode == 2) off = a_chunk_offset(n, k >> 2) + (k & 3) * 4;                           // K-major SW128, rows = n
+    else if (P.mode == 4) off = (uint32_t)((n >> 2) * 128 + (k >> 3) * 2048 + (k & 7) * 16 + (n & 3) * 4);   // MN-major, no swizzle: core = 8 k x 16 B; SBO=128 (next 4 n), LBO=2048 (next 8 k)
+    else if (P.mode == 5 || P.mode == 6) off = (uint32_t)((n >> 5) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + ((((n & 31) >> 3) ^ (k & 3)) << 5) + (n & 7) * 4);  // MN-major SW128_BASE32B: atom 4 k x 128 B
+    else if (P.mode == 7) off = (uint32_t)((n >> 5) * 4096 + (k >> 3) * 1024 + (k & 7) * 128 + ((((n & 31) >> 3) ^ (k & 3)) << 5) + (n & 7) * 4);  // BASE32B with 8-row atoms
     else off = (uint32_t)((n >> 3) * 128 + (n & 7) * 16 + (k >> 2) * 1024 + (k & 3) * 4);          // K-major no swizzle: SBO=128, LBO=1024
     *reinterpret_cast<float*>(b_tile + off) = v;
   }
@@ -65,6 +68,10 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(ProbeArgs P) {
         if (P.mode == 0) { ad = umma_desc(a_base + kg * 32, 16, 1024); bd = umma_desc(b_base + kg * 1024, 4096, 1024); idesc = umma_idesc_tf32(64) | (1u << 16); }
         else if (P.mode == 1) { ad = umma_desc(a_base + kg * 32, 16, 1024); bd = umma_desc(b_base + kg * 1024, 1024, 4096); idesc = umma_idesc_tf32(64) | (1u << 16); }
         else if (P.mode == 2) { ad = umma_desc(a_base + kg * 32, 16, 1024); bd = umma_desc(b_base + kg * 32, 16, 1024); idesc = umma_idesc_tf32(64); }
+        else if (P.mode == 4) { ad = umma_desc(a_base + kg * 32, 16, 1024); bd = umma_desc(b_base + kg * 2048, 2048, 128) & ~((uint64_t)7 << 61); idesc = umma_idesc_tf32(64) | (1u << 16); }
+        else if (P.mode == 5) { ad = umma_desc(a_base + kg * 32, 16, 1024); bd = (umma_desc(b_base + kg * 1024, 4096, 512) & ~((uint64_t)7 << 61)) | ((uint64_t)1 << 61); idesc = umma_idesc_tf32(64) | (1u << 16); }
+        else if (P.mode == 6) { ad = umma_desc(a_base + kg * 32, 16, 1024); bd = (umma_desc(b_base + kg * 1024, 512, 4096) & ~((uint64_t)7 << 61)) | ((uint64_t)1 << 61); idesc = umma_idesc_tf32(64) | (1u << 16); }
+        else if (P.mode == 7) { ad = umma_desc(a_base + kg * 32, 16, 1024); bd = (umma_desc(b_base + kg * 1024, 4096, 1024) & ~((uint64_t)7 << 61)) | ((uint64_t)1 << 61); idesc = umma_idesc_tf32(64) | (1u << 16); }
         else {
           ad = umma_desc(a_base + kg * 4096, 2048, 128) & ~((uint64_t)7 << 61);
           bd = umma_desc(b_base + kg * 2048, 1024, 128) & ~((uint64_t)7 << 61);
@@ -99,7 +106,7 @@ int main() {
   cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  for (int mode = 0; mode < 4; ++mode) {
+  for (int mode = 2; mode < 8; ++mode) {
     for (int ksteps = 1; ksteps <= 4; ksteps += 3) {
       cudaMemset(dd, 0xff, d.size() * 4);
       ProbeArgs P{mode, ksteps, dd, da, db};
