@@ -179,6 +179,27 @@ __device__ __forceinline__ uint64_t umma_desc_b(uint32_t smem_addr) {
   return d;
 }
 
+// Squared distance for the dense path: no mask is decided on it, so plain (FMA-contracted) arithmetic is fine.
+template <int GEO>
+__device__ __forceinline__ float dist2_fast(const Point<GEO>& a, float bx, float by, float period) {
+  if (GEO == GEO_EUCLID1) {
+    const float dx = a.x - bx;
+    return dx * dx;
+  } else if (GEO == GEO_EUCLID2) {
+    const float dx = a.x - bx, dy = a.y - by;
+    return fmaf(dy, dy, dx * dx);
+  } else if (GEO == GEO_PERIODIC1) {
+    float m = fabsf(a.x - bx);
+    m = fminf(m, period - m);
+    return m * m;
+  } else {
+    float mx = fabsf(a.x - bx), my = fabsf(a.y - by);
+    mx = fminf(mx, period - mx);
+    my = fminf(my, period - my);
+    return fmaf(my, my, mx * mx);
+  }
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -261,20 +282,22 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
       const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : h_fixed;
       const int k0 = (kb % kb_per_head) * DENSE_KB;
       const float sc2 = __ldg(P.scale + h) * LOG2E;
-      // the 32 reduced points of this block (per-warp copy: no block-level sync needed)
+      // the 32 reduced points of this block (per-warp copy: no block-level sync needed): (x, y, shift*sc2, post).
+      // Points past the end sit at infinity, so their weight is exp2(-inf) = 0 without any predicate.
       {
         const int k = k0 + lane;
         const bool ok = k < P.n_red;
         const Point<GEO> q = load_point<GEO>(mesh_red, ok ? k : 0, P.sd);
-        float vm = 0.f, post = ok ? 1.f : 0.f;
+        float bias = 0.f, post = 1.f;
         if (MODE == DENSE_DVALUES && ok) {
-          vm = __ldg(P.v_min + (int64_t)sample * P.N + k);
+          bias = __ldg(P.v_min + (int64_t)sample * P.N + k) * sc2;
           post = 1.f / __ldg(P.rowsum + ((int64_t)sample * P.H + h) * P.N + k);
         }
         __syncwarp();
-        my_pts[lane] = make_float4(q.x, q.y, vm, post);
+        my_pts[lane] = make_float4(ok ? q.x : INFINITY, q.y, bias, post);
         __syncwarp();
       }
+      const float my_bias = own_vmin * sc2;
       mbar_wait(&empty_bar[s], (use & 1) ^ 1);
       unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES;
 #pragma unroll
@@ -283,18 +306,14 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float4 q = my_pts[c * 4 + e];
-          Point<GEO> other;
-          other.x = q.x;
-          other.y = q.y;
-          const float d2 = (MODE == DENSE_DVALUES) ? dist2<GEO>(other, me, period) : dist2<GEO>(me, other, period);
-          const float vm = (MODE == DENSE_DVALUES) ? q.z : own_vmin;
-          float p = fast_exp2((vm - d2) * sc2) * q.w;
-          if (!own_ok) p = 0.f;
+          const float d2 = dist2_fast<GEO>(me, q.x, q.y, period);
+          float p = fast_exp2(fmaf(-d2, sc2, (MODE == DENSE_DVALUES) ? q.z : my_bias));
+          if (MODE == DENSE_DVALUES) p *= q.w;
           lsum += p;
           hi[e] = tf32_hi(p);
           lo[e] = p - hi[e];
           if (MODE == DENSE_DSCALE) {
-            const float pd = p * d2;
+            const float pd = (d2 < INFINITY) ? p * d2 : 0.f;
             msum += pd;
             hid[e] = tf32_hi(pd);
             lod[e] = pd - hid[e];
