@@ -49,9 +49,12 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
   for (int r = 1; r < R; ++r) mn = min(mn, key[r]);
   mn = __reduce_min_sync(FULL, mn);
 
-  // k_lo-th smallest key, most significant bit first.
+  // k_lo-th smallest key, most significant bit first.  `cand` counts the keys that still match the decided
+  // bits; once a single candidate is left it is the answer and the remaining bit steps are skipped (on meshes
+  // without exact ties this happens after ~log2(M) + a few steps instead of 32).
   uint32_t prefix = 0;
   int k = P.k_lo;
+  int cand = R * 32;
 #pragma unroll 1
   for (int bit = 31; bit >= 0; --bit) {
     int c = 0;
@@ -61,6 +64,18 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
     if (k >= c) {
       k -= c;
       prefix |= 1u << bit;
+      cand -= c;
+    } else {
+      cand = c;
+    }
+    if (cand == 1 && bit > 0) {
+      // the unique key that agrees with `prefix` on bits [bit, 31]
+      uint32_t mine = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (((key[r] ^ prefix) >> bit) == 0u) mine = key[r];
+      prefix = __reduce_or_sync(FULL, mine);
+      break;
     }
   }
   const uint32_t lo = prefix;

@@ -142,7 +142,8 @@ class _MeshCache:
     every row each time (pit.py:136).  An entry is keyed by the storage address, offset, shape, strides
     and autograd version of both incoming tensors and keeps a strong reference to them, so the address
     cannot be recycled while the entry lives and any in-place write (which bumps the version) misses.
-    Per-sample meshes (posatt / posatt_cross) change every batch and are never cached.
+    Per-sample meshes (posatt / posatt_cross) change every batch; their entries serve the repeated uses inside
+    one step (processor blocks, backward) and are evicted in insertion order.
     """
 
     def __init__(self, capacity: int = 32):
@@ -183,6 +184,10 @@ def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
     """(v_min, v_lo, v_hi, w, masked): order statistics replacing torch.quantile's row sort (uncached)."""
     masked = locality < 1.0
     k_lo, k_hi, w = _cabi.quantile_ranks(locality, st.M) if masked else (0, 0, 0.0)
+    if not masked and mesh_out.data_ptr() == mesh_in.data_ptr() and mesh_out.shape == mesh_in.shape:
+        # global self stage: the row minimum is d2(i, i) = 0 exactly, no statistics needed
+        zeros = torch.zeros(st.stat_shape(), dtype=torch.float32, device=st.device)
+        return zeros, zeros, zeros, w, masked
     stats = torch.empty((3,) + st.stat_shape(), dtype=torch.float32, device=st.device)
     with _timed("rowstat", st, False):
         _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
@@ -193,8 +198,12 @@ def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
 
 def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, locality: float):
     """Contiguous meshes, the validated stage, the wrap period and the row statistics -- cached for shared meshes."""
-    batched = mesh_in.dim() == 3
-    cacheable = mesh_cache.enabled and not batched and mesh_in.is_cuda
+    # Shared meshes hit across steps; per-sample meshes hit within a step (the four processor blocks and the
+    # backward see the same tensors).  The strong reference held by an entry keeps the address from being recycled.
+    capturing = mesh_in.is_cuda and torch.cuda.is_current_stream_capturing()
+    # inside a CUDA-graph capture per-sample meshes are graph inputs whose contents change between replays:
+    # their statistics must be recomputed by captured kernels, never taken from the cache
+    cacheable = mesh_cache.enabled and mesh_in.is_cuda and not (capturing and mesh_in.dim() == 3)
     key = mesh_cache.key(mesh_out, mesh_in, variant, locality) if cacheable else None
     hit = mesh_cache.get(key) if cacheable else None
     if hit is not None:
@@ -206,7 +215,7 @@ def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, localit
         period = wrap_period(mi, variant)
         stats = row_statistics(st, mo, mi, period, float(locality))
     # entries created while a CUDA graph is being captured would point into the graph's private pool: do not keep them
-    if cacheable and not torch.cuda.is_current_stream_capturing():
+    if cacheable and not capturing:
         mesh_cache.put(key, (mo, mi, period, stats), (mesh_out, mesh_in))
     return mo, mi, st, period, stats
 
