@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -110,6 +110,16 @@ def algorithmic_bytes(key) -> int:
     else:                          # rowstat: coordinates in, three floats per row out
         words = meshes + 3 * N * (B if batched else 1)
     return 4 * words
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch of a position-attention call from the committed ncu captures (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    table = json.load(open(path))
+    tag, _variant, _batched, B, H, N, M, D, _sd, _concat = key
+    return table.get(f"{tag}:B{B}:H{H}:N{N}:M{M}:D{D}")
 
 
 def load_peaks():
@@ -253,12 +263,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident measurement ----
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()          # sampled from the warm-up on (20 ms period): the timed region itself can be < 100 ms
     for i in range(args.warmup):
         step(*resident[i % n_buf])
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
@@ -319,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
             q = algorithmic_bytes(top)
             ach = q / (kernels[top]["ms_avg"] * 1e-3) / 1e9
             share = kernels[top]["ms_avg"] * kernels[top]["calls"] / k_steps / (ms / args.steps)
-            roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic(top),
                         "kernel": {"call": top[0], "variant": top[1], "mesh_batched": bool(top[2]), "B": top[3], "H": top[4],
                                    "N": top[5], "M": top[6], "D": top[7]},
                         "algorithmic_bytes_per_launch": q, "avg_launch_ms": kernels[top]["ms_avg"],
