@@ -109,6 +109,25 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
                         float* d_values, float* d_scale, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* Fused decoder tail: pit.decoder (pit.py:124-127) = cross position-attention `up` + kaiming_mlp `de`
+ * (pit.py:21-26), for shared meshes with M <= 1024, H <= 2, hidden width C a power of two in [32, 512], out_dim <= 4.
+ * problem->dim is the hidden width C.  The first Linear is pushed through the (linear) attention by the caller:
+ *   y [B,M,H,C]  with  y[b,j,h,:] = W1[:, h*D:(h+1)*D] @ U[b,j,:]        (W1 = de.mlp1.weight, U = latent features)
+ *   out[b,n,o]  = b2[o] + sum_c W2[o,c] * gelu(b1[c] + sum_h sum_j A_h[n,j] * y[b,j,h,c])      (exact erf GELU)
+ * so nothing of size N x H*D or N x C is ever written to memory.  rowsum [H,N] is saved for the backward, which
+ * returns d_y [B,M,H,C] (dW1 and dU follow from it through the caller's GEMM), d_scale [H], d_b1 [C], d_w2 [O,C],
+ * d_b2 [O]; every gradient buffer is overwritten. */
+int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim);
+int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
+                             const float* period, const float* y, const float* scale,
+                             const pit_rowstat_t* stat, const float* b1, const float* w2, const float* b2,
+                             int32_t out_dim, float* out, float* rowsum, void* stream);
+int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
+                              const float* period, const float* y, const float* scale,
+                              const pit_rowstat_t* stat, const float* b1, const float* w2, const float* b2,
+                              int32_t out_dim, const float* rowsum, const float* d_out, float* d_y,
+                              float* d_scale, float* d_b1, float* d_w2, float* d_b2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

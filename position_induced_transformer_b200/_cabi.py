@@ -18,6 +18,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
     "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward",
+    "pit_decoder_tail_supported", "pit_decoder_tail_forward", "pit_decoder_tail_backward",
 )
 
 
@@ -49,6 +50,11 @@ def _load() -> C.CDLL:
                                        f32p, i64, i64, i32, f32p, p, C.c_size_t, p]
     lib.pit_posatt_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat), f32p,
                                         f32p, i64, i64, i32, f32p, f32p, p, C.c_size_t, p]
+    lib.pit_decoder_tail_supported.argtypes = [C.POINTER(Problem), i32]
+    lib.pit_decoder_tail_forward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
+                                             f32p, f32p, f32p, i32, f32p, f32p, p]
+    lib.pit_decoder_tail_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
+                                              f32p, f32p, f32p, i32, f32p, f32p, f32p, f32p, f32p, f32p, f32p, p]
     if lib.pit_abi_version() != ABI_VERSION:
         raise ImportError(f"libpit_posatt.so ABI {lib.pit_abi_version()} != expected {ABI_VERSION}; rebuild it")
     return lib

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <type_traits>
 
+#include "decoder_tail.cuh"
 #include "dense_attention.cuh"
 #include "tall_attention.cuh"
 #include "wide_attention.cuh"
@@ -480,6 +481,104 @@ cudaError_t dense_launch(int geo, const pit_problem_t* p, const pit::DenseParams
   return pick(Int<pit::GEO_PERIODIC2>{});
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused decoder tail (shared meshes, M <= 1024, H <= 2, hidden width a power of two in [32, 512], out_dim <= 4)
+// ---------------------------------------------------------------------------------------------
+bool tail_eligible(const pit_problem_t* p, int out_dim) {
+  const int c = p->dim;
+  return tall_eligible(p) && c >= 32 && c <= 512 && (c & (c - 1)) == 0 && out_dim >= 1 && out_dim <= pit::TAIL_MAX_OUT;
+}
+
+TallPlan plan_tail_fwd(const pit_problem_t* p) {
+  TallPlan c = plan_tall_fwd(p);  // same row partition; lanes4 = B*C/4 (dim holds the hidden width)
+  const int k_per_b = p->dim / 4 > 32 ? p->dim / 128 : 1;
+  if (c.ok && c.l4 % k_per_b != 0) c.l4 = 4;
+  if (c.ok) c.chunks = (c.lanes4 + 32 * c.l4 - 1) / (32 * c.l4);
+  if (c.ok) c.smem += (size_t)p->dim * (1 + pit::TAIL_MAX_OUT) * sizeof(float);  // b1 and W2 behind the entry segments
+  return c;
+}
+
+TallPlan plan_tail_bwd(const pit_problem_t* p) {
+  TallPlan c{};
+  if (!tall_eligible(p)) return c;
+  c.lanes4 = p->batch * p->dim / 4;
+  if (c.lanes4 > 4 * pit::TALL_THREADS) return c;
+  c.l4 = (c.lanes4 + pit::TALL_THREADS - 1) / pit::TALL_THREADS;
+  if (c.l4 == 3) c.l4 = 4;
+  c.cpl = cpl_of(p->n_in);
+  const int budget = max_smem_optin();
+  const int per_slot = p->n_head * c.lanes4 * 16;
+  c.n_slots = 48 * 1024 / per_slot;
+  if (c.n_slots > 64) c.n_slots = 64;
+  if (c.n_slots > p->n_in) c.n_slots = p->n_in;
+  if (c.n_slots < 4) return c;
+  c.smem = pit::tail_bwd_smem_bytes(c.cpl, p->n_in, c.lanes4, p->n_head, c.n_slots);
+  if (c.smem > (size_t)budget - 1024) return c;
+  int per_sm = (int)((size_t)budget / (c.smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const int target = sm_count() * per_sm;
+  int rows = (p->n_out + target - 1) / target;
+  rows = (rows + pit::TALL_WARPS - 1) / pit::TALL_WARPS * pit::TALL_WARPS;
+  c.rows_per_unit = rows;
+  c.grid = (p->n_out + rows - 1) / rows;
+  c.chunks = 1;
+  c.ok = true;
+  return c;
+}
+
+pit::TailParams tail_params(const pit_problem_t* p, const TallPlan& c, const float* mesh_out, const float* mesh_in,
+                            const float* period, const float* y, const float* scale, const pit_rowstat_t* st,
+                            const float* b1, const float* w2, const float* b2, int out_dim) {
+  pit::TailParams P{};
+  P.mesh_out = mesh_out;
+  P.mesh_in = mesh_in;
+  P.period = p->variant == PIT_EUCLID ? nullptr : period;
+  P.y = y;
+  P.scale = scale;
+  P.v_min = st->v_min;
+  P.v_lo = st->v_lo;
+  P.v_hi = st->v_hi;
+  P.weight = st->weight;
+  P.masked = st->masked;
+  P.B = p->batch;
+  P.H = p->n_head;
+  P.N = p->n_out;
+  P.M = p->n_in;
+  P.C = p->dim;
+  P.O = out_dim;
+  P.sd = p->space_dim;
+  P.lanes4 = c.lanes4;
+  P.rows_per_unit = c.rows_per_unit;
+  P.n_slots = c.n_slots;
+  P.b1 = b1;
+  P.w2 = w2;
+  P.b2 = b2;
+  return P;
+}
+
+template <typename K>
+cudaError_t tail_launch(K kernel, const TallPlan& c, const pit::TailParams& P, cudaStream_t st) {
+  if (c.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) return e;
+  }
+  kernel<<<dim3(c.grid, c.chunks), pit::TALL_THREADS, c.smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t tail_forward(int geo, const TallPlan& plan, const pit::TailParams& P, cudaStream_t st) {
+  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
+    return tail_launch(pit::tail_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value, decltype(l)::value>, plan, P, st);
+  });
+}
+cudaError_t tail_backward(int geo, const TallPlan& plan, const pit::TailParams& P, cudaStream_t st) {
+  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
+    return tail_launch(pit::tail_bwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value, decltype(l)::value>, plan, P, st);
+  });
+}
+
 // Sum of the per-row scale-gradient terms of one head (generic path): d_scale[h] = sum_rows rows[row*H + h].
 __global__ void reduce_scale_rows_kernel(const float* __restrict__ rows, int64_t n_rows, int H, float* __restrict__ d_scale) {
   __shared__ float red[32];
@@ -783,6 +882,65 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
     PIT_DISPATCH(pit::posatt_dvalues_kernel, geo, s.vec, s.a, <<<grid, block, 0, st>>>(P));
     PIT_LAUNCHED();
   }
+  return PIT_OK;
+}
+
+
+int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim) {
+  if (check_problem(p) != PIT_OK) return 0;
+  if (!tail_eligible(p, out_dim)) return 0;
+  return plan_tail_fwd(p).ok && plan_tail_bwd(p).ok ? 1 : 0;
+}
+
+int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                             const float* y, const float* scale, const pit_rowstat_t* stat, const float* b1, const float* w2,
+                             const float* b2, int32_t out_dim, float* out, float* rowsum, void* stream) {
+  if (int rc = check_problem(p)) return rc;
+  if (!mesh_out || !mesh_in || !y || !scale || !b1 || !w2 || !b2 || !out || !rowsum) return fail(PIT_ERR_ARG, "null pointer");
+  if (int rc = check_stat(p, stat, period)) return rc;
+  if (!tail_eligible(p, out_dim)) return fail(PIT_ERR_ARG, "decoder tail: unsupported configuration (see pit_decoder_tail_supported)");
+  if (!aligned16(y) || !aligned16(b1) || !aligned16(w2)) return fail(PIT_ERR_ARG, "decoder tail: y, b1, w2 must be 16-byte aligned");
+  const TallPlan plan = plan_tail_fwd(p);
+  if (!plan.ok) return fail(PIT_ERR_ARG, "decoder tail: no launch plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
+  P.out = out;
+  P.rowsum = rowsum;
+  PIT_CUDA(tail_forward(geo_of(p), plan, P, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
+int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                              const float* y, const float* scale, const pit_rowstat_t* stat, const float* b1, const float* w2,
+                              const float* b2, int32_t out_dim, const float* rowsum, const float* d_out, float* d_y,
+                              float* d_scale, float* d_b1, float* d_w2, float* d_b2, void* stream) {
+  if (int rc = check_problem(p)) return rc;
+  if (!mesh_out || !mesh_in || !y || !scale || !b1 || !w2 || !b2 || !rowsum || !d_out || !d_y || !d_scale || !d_b1 || !d_w2 || !d_b2)
+    return fail(PIT_ERR_ARG, "null pointer");
+  if (int rc = check_stat(p, stat, period)) return rc;
+  if (!tail_eligible(p, out_dim)) return fail(PIT_ERR_ARG, "decoder tail: unsupported configuration (see pit_decoder_tail_supported)");
+  if (!aligned16(y) || !aligned16(b1) || !aligned16(w2) || !aligned16(d_y) || !aligned16(d_b1) || !aligned16(d_w2))
+    return fail(PIT_ERR_ARG, "decoder tail: y, b1, w2 and their gradients must be 16-byte aligned");
+  const TallPlan plan = plan_tail_bwd(p);
+  if (!plan.ok) return fail(PIT_ERR_ARG, "decoder tail: no launch plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
+  P.rowsum = const_cast<float*>(rowsum);
+  P.d_out = d_out;
+  P.d_y = d_y;
+  P.d_scale = d_scale;
+  P.d_b1 = d_b1;
+  P.d_w2 = d_w2;
+  P.d_b2 = d_b2;
+  const size_t c = (size_t)p->dim;
+  PIT_CUDA(cudaMemsetAsync(d_y, 0, (size_t)p->batch * p->n_in * p->n_head * c * sizeof(float), st));
+  PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
+  PIT_CUDA(cudaMemsetAsync(d_b1, 0, c * sizeof(float), st));
+  PIT_CUDA(cudaMemsetAsync(d_w2, 0, (size_t)out_dim * c * sizeof(float), st));
+  PIT_CUDA(cudaMemsetAsync(d_b2, 0, (size_t)out_dim * sizeof(float), st));
+  PIT_CUDA(tail_backward(geo_of(p), plan, P, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }
 

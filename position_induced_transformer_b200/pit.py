@@ -24,10 +24,10 @@ from torch.nn.functional import gelu
 np.random.seed(0)
 from math import pi
 
-from .posatt import position_attention
+from .posatt import decoder_tail, decoder_tail_supported, position_attention
 
 __all__ = [
-    "torch", "nn", "gelu", "np", "pi", "kaiming_mlp", "use_host_scale_map",
+    "torch", "nn", "gelu", "np", "pi", "kaiming_mlp", "use_host_scale_map", "use_fused_decoder_tail",
     "posatt", "posatt_cross", "pit",
     "posatt_fixed", "posatt_cross_fixed", "pit_fixed",
     "posatt_periodic1d", "posatt_cross_periodic1d", "pit_periodic1d",
@@ -151,6 +151,16 @@ class posatt_cross_periodic2d(posatt_periodic2d):
     _cross = True
 
 
+_FUSABLE_CROSS = (posatt_cross_fixed, posatt_cross_periodic1d, posatt_cross_periodic2d)
+_FUSED_DECODER_TAIL = True
+
+
+def use_fused_decoder_tail(enabled: bool) -> None:
+    """Switch the fused decoder tail (attention + MLP in one kernel) on or off; off runs `de(up(...))` as two ops."""
+    global _FUSED_DECODER_TAIL
+    _FUSED_DECODER_TAIL = bool(enabled)
+
+
 class pit(nn.Module):
     """Encoder / processor / decoder container (pit.py:73-127).  Scripts subclass it and add ``forward``."""
 
@@ -197,7 +207,15 @@ class pit(nn.Module):
         return func_ltt
 
     def decoder(self, mesh_ltt, func_ltt, mesh_out):
-        return self.de(self.up(mesh_out, mesh_ltt, func_ltt))
+        up, de = self.up, self.de
+        # Fused tail: attention + both Linears + GELU in one kernel, nothing N x (H*D) wide is written to memory.
+        # Only taken for the stock layer types on a shared mesh; anything customised runs the two modules as written.
+        if (_FUSED_DECODER_TAIL and type(up) in _FUSABLE_CROSS and type(de) is kaiming_mlp and mesh_ltt.dim() == 2
+                and func_ltt.is_cuda and func_ltt.dim() == 3 and de.mlp1.in_features == up.n_head * func_ltt.shape[-1]
+                and decoder_tail_supported(mesh_ltt, func_ltt, up.n_head, de.mlp1.out_features, de.mlp2.out_features)):
+            return decoder_tail(mesh_out, mesh_ltt, func_ltt, head_scale(up.lmda), up.locality, de.mlp1.weight, de.mlp1.bias,
+                                de.mlp2.weight, de.mlp2.bias, variant=up._variant)
+        return de(up(mesh_out, mesh_ltt, func_ltt))
 
 
 class pit_fixed(pit):

@@ -297,3 +297,80 @@ def position_attention(mesh_out: torch.Tensor, mesh_in: torch.Tensor, values: to
     """
     return _PositionAttention.apply(values, scale, mesh_out, mesh_in, scale.numel(), float(locality), variant,
                                     bool(self_concat))
+
+
+# ----------------------------------------------------------------------------------------------
+# fused decoder tail: cross position-attention + two-layer MLP (pit.decoder, pit.py:124-127)
+# ----------------------------------------------------------------------------------------------
+class _DecoderTail(torch.autograd.Function):
+    """out = W2 gelu(b1 + sum_h A_h Y_h) + b2 with Y = first Linear applied on the latent mesh (see decoder_tail)."""
+
+    @staticmethod
+    def forward(ctx, y, scale, b1, w2, b2, mesh_out, mesh_in, locality, variant):
+        y = y.contiguous()                                   # (B, M, H, C)
+        B, M, H, Cw = y.shape
+        scale_shape = scale.shape
+        scale = scale.reshape(-1).contiguous()
+        b1, w2, b2 = b1.contiguous(), w2.contiguous(), b2.contiguous()
+        out_dim = w2.shape[0]
+        # the stage descriptor treats the hidden width as the value width
+        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked) = prepare_meshes(
+            mesh_out, mesh_in, y.reshape(B, M, H * Cw)[:, :, :Cw], H, variant, float(locality))
+        st.problem.dim = Cw
+        with torch.cuda.device(st.device):
+            out = torch.empty((B, st.N, out_dim), dtype=torch.float32, device=st.device)
+            rowsum = torch.empty((H, st.N), dtype=torch.float32, device=st.device)
+            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
+            with _timed("tail_fwd", st, False):
+                _cabi.check(_cabi.lib.pit_decoder_tail_forward(
+                    C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), y.data_ptr(), scale.data_ptr(),
+                    C.byref(rs), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out_dim, out.data_ptr(), rowsum.data_ptr(),
+                    _stream(st.device)), "pit_decoder_tail_forward")
+        ctx.save_for_backward(y, scale, b1, w2, b2, mesh_out, mesh_in, period if period is not None else scale.new_empty(0),
+                              v_min, v_lo, v_hi, rowsum)
+        ctx.meta = (variant, w, masked, scale_shape, out_dim)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        y, scale, b1, w2, b2, mesh_out, mesh_in, period, v_min, v_lo, v_hi, rowsum = ctx.saved_tensors
+        variant, w, masked, scale_shape, out_dim = ctx.meta
+        period = period if period.numel() else None
+        B, M, H, Cw = y.shape
+        st = _Stage(mesh_out, mesh_in, y.reshape(B, M, H * Cw)[:, :, :Cw], H, variant)
+        st.problem.dim = Cw
+        d_out = d_out.contiguous()
+        with torch.cuda.device(st.device):
+            d_y = torch.empty_like(y)
+            d_scale = torch.empty(H, dtype=torch.float32, device=st.device)
+            d_b1, d_w2, d_b2 = torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
+            with _timed("tail_bwd", st, False):
+                _cabi.check(_cabi.lib.pit_decoder_tail_backward(
+                    C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), y.data_ptr(), scale.data_ptr(),
+                    C.byref(rs), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out_dim, rowsum.data_ptr(), d_out.data_ptr(),
+                    d_y.data_ptr(), d_scale.data_ptr(), d_b1.data_ptr(), d_w2.data_ptr(), d_b2.data_ptr(), _stream(st.device)),
+                    "pit_decoder_tail_backward")
+        return d_y, d_scale.reshape(scale_shape), d_b1, d_w2, d_b2, None, None, None, None
+
+
+def decoder_tail_supported(mesh_in: torch.Tensor, values: torch.Tensor, n_head: int, hidden: int, out_dim: int) -> bool:
+    """True when the fused decoder-tail kernels cover this configuration (shared mesh, M <= 1024, H <= 2, ...)."""
+    if mesh_in.dim() != 2 or not values.is_cuda or values.dtype != torch.float32:
+        return False
+    prob = _cabi.Problem(0, mesh_in.shape[-1], 0, values.shape[0], n_head, 1, mesh_in.shape[0], hidden)
+    return bool(_cabi.lib.pit_decoder_tail_supported(C.byref(prob), out_dim))
+
+
+def decoder_tail(mesh_out, mesh_in, values, scale, locality, w1, b1, w2, b2, variant: str = "euclid") -> torch.Tensor:
+    """Fused `de(up(mesh_out, mesh_in, values))`: (B, M, D) latent features -> (B, N, out_dim).
+
+    w1 (C, H*D), b1 (C), w2 (O, C), b2 (O) are the parameters of the two Linears of ``kaiming_mlp``.  The first
+    Linear is applied on the latent mesh -- Y[b,j,h,:] = W1[:, hD:(h+1)D] U[b,j,:] -- which is exact because
+    position-attention is linear in its values; gradients of w1 and of the features flow through this einsum.
+    """
+    B, M, D = values.shape
+    H = scale.numel()
+    Cw = w1.shape[0]
+    y = torch.einsum("bjd,chd->bjhc", values, w1.reshape(Cw, H, D))
+    return _DecoderTail.apply(y, scale, b1, w2, b2, mesh_out, mesh_in, float(locality), variant)

@@ -1,0 +1,94 @@
+"""Fused decoder tail (attention + two-layer MLP in one kernel) against the CPU oracle's decode()."""
+import pytest
+import torch
+
+from conftest import rel_linf
+from oracle import pit_oracle, posatt_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(variant, sd, N, M, B, D, H, Cw, O, q, seed):
+    g = torch.Generator().manual_seed(seed)
+    if variant == "periodic1d":
+        mesh_out = torch.linspace(0, 1, N + 1)[:-1].reshape(-1, 1)
+        mesh_in = torch.linspace(0, 1, M + 1)[:-1].reshape(-1, 1)
+    elif variant == "periodic2d":
+        import numpy as np
+        def grid(n):
+            ax = np.linspace(0, 1, n + 1)[:-1]
+            return torch.tensor(np.vstack([m.ravel() for m in np.meshgrid(ax, ax)]).T, dtype=torch.float)
+        mesh_out, mesh_in = grid(int(N ** 0.5)), grid(int(M ** 0.5))
+    else:
+        mesh_out, mesh_in = torch.rand(N, sd, generator=g), torch.rand(M, sd, generator=g)
+    p = {
+        "up.lmda": torch.rand(H, 1, 1, generator=g) * 2 - 0.5,
+        "de.mlp1.weight": torch.randn(Cw, H * D, generator=g) / (H * D) ** 0.5,
+        "de.mlp1.bias": torch.randn(Cw, generator=g) * 0.1,
+        "de.mlp2.weight": torch.randn(O, Cw, generator=g) / Cw ** 0.5,
+        "de.mlp2.bias": torch.randn(O, generator=g) * 0.1,
+    }
+    feats = torch.randn(B, M, D, generator=g)
+    return mesh_out, mesh_in, feats, p, g
+
+
+@pytest.mark.parametrize("variant,sd,N,M,B,D,H,Cw,O,q", [
+    ("euclid", 2, 700, 256, 8, 64, 2, 64, 1, 0.02),      # Darcy-like
+    ("euclid", 1, 500, 256, 8, 32, 1, 32, 3, 0.02),      # Sod-like
+    ("periodic1d", 1, 512, 128, 4, 64, 2, 64, 1, 0.05),  # Burgers-like
+    ("periodic2d", 2, 1024, 64, 2, 32, 2, 256, 2, 0.1),  # wide hidden layer: one sample spans two register groups
+    ("euclid", 2, 300, 100, 3, 16, 2, 128, 4, 1.0),      # unmasked
+    ("euclid", 2, 97, 40, 1, 8, 1, 512, 1, 0.2),
+])
+def test_decoder_tail_matches_oracle(variant, sd, N, M, B, D, H, Cw, O, q, cuda_device, host_scale_map):
+    import position_induced_transformer_b200.pit as pit_mod
+    from position_induced_transformer_b200.posatt import decoder_tail, decoder_tail_supported
+    mesh_out, mesh_in, feats, p, g = _case(variant, sd, N, M, B, D, H, Cw, O, q, seed=N + M + Cw)
+    # oracle
+    pc = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    fc = feats.clone().requires_grad_(True)
+    want = pit_oracle.decode(pc, variant, mesh_in, fc, mesh_out, q)
+    up = torch.randn(want.shape, generator=g)
+    want.backward(up)
+    # fused
+    dev = cuda_device
+    pg = {k: v.clone().to(dev).requires_grad_(True) for k, v in p.items()}
+    fg = feats.clone().to(dev).requires_grad_(True)
+    assert decoder_tail_supported(mesh_in.to(dev), fg, H, Cw, O)
+    prev = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("highest")
+    try:
+        got = decoder_tail(mesh_out.to(dev), mesh_in.to(dev), fg, pit_mod.head_scale(pg["up.lmda"]), q,
+                           pg["de.mlp1.weight"], pg["de.mlp1.bias"], pg["de.mlp2.weight"], pg["de.mlp2.bias"], variant=variant)
+        got.backward(up.to(dev))
+    finally:
+        torch.set_float32_matmul_precision(prev)
+    assert got.shape == want.shape
+    assert rel_linf(got.detach().cpu(), want.detach()) <= 1e-5
+    assert rel_linf(fg.grad.cpu(), fc.grad) <= 1e-4
+    for k in p:
+        assert rel_linf(pg[k].grad.cpu(), pc[k].grad, floor=1e-6) <= 1e-4, k
+
+
+def test_pit_decoder_uses_the_fused_tail(cuda_device, host_scale_map):
+    """pit.decoder takes the fused path for the stock layers and equals the two-module composition."""
+    import position_induced_transformer_b200.pit as pit_mod
+    from position_induced_transformer_b200 import _cabi, workloads
+    torch.manual_seed(0)
+    w = workloads.make_darcy(43, batch=2).to(cuda_device)
+    gen = torch.Generator().manual_seed(3)
+    latent = torch.randn(2, 256, 64, generator=gen).to(cuda_device)
+    mesh = w.meshes[0].reshape(-1, 2)
+    prev = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("highest")
+    try:
+        n0 = _cabi.launch_count()
+        fused = w.model.decoder(w.model.mesh_ltt, latent, mesh)
+        fused_launches = _cabi.launch_count() - n0
+        pit_mod.use_fused_decoder_tail(False)
+        plain = w.model.decoder(w.model.mesh_ltt, latent, mesh)
+        pit_mod.use_fused_decoder_tail(True)
+    finally:
+        torch.set_float32_matmul_precision(prev)
+    assert fused_launches == 1
+    assert rel_linf(fused, plain) <= 1e-5
