@@ -88,7 +88,7 @@ __device__ __forceinline__ float seg_sum(float v, int seg) {
 template <int GEO, int CPL, int NH, int L4>
 __global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams P) {
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
-  constexpr int G = (L4 >= 4) ? 1 : (4 / L4);  // entries per gather batch (NH * L4 * G loads in flight)
+  constexpr int G = (NH * L4 >= 8) ? 2 : (8 / (NH * L4));  // entries per gather batch: >= 8 independent 128-bit loads in flight
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* seg = reinterpret_cast<float4*>(tall_smem_raw) + (size_t)warp * (CPL * 32);
   const float period = P.period ? __ldg(P.period) : 0.f;
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams
 
   const int c4_per_b = P.C / 4;
   const int segw = c4_per_b < 32 ? c4_per_b : 32;
-  int64_t y_off[L4];
+  // Lane -> (sample, channel) bookkeeping as 32-bit element offsets (the host guarantees B*M*H*C < 2^31); lanes past
+  // the end are clamped onto the last valid lane so that every gather is unconditional, and only skip the final store.
+  int y_off[L4];
   int bidx[L4], cidx[L4];
   bool ok[L4];
   // b1 and W2 live in shared memory behind the per-warp entry segments: [b1 (C) | W2 (O x C)]
@@ -114,12 +116,15 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < L4; ++k) {
-    const int q = (blockIdx.y * L4 + k) * 32 + lane;
+    int q = (blockIdx.y * L4 + k) * 32 + lane;
     ok[k] = q < P.lanes4;
-    bidx[k] = ok[k] ? q / c4_per_b : 0;
-    cidx[k] = ok[k] ? (q - bidx[k] * c4_per_b) * 4 : 0;
-    y_off[k] = (int64_t)bidx[k] * P.M * NH * P.C + cidx[k];
+    q = min(q, P.lanes4 - 1);
+    bidx[k] = q / c4_per_b;
+    cidx[k] = (q - bidx[k] * c4_per_b) * 4;
+    y_off[k] = bidx[k] * P.M * NH * P.C + cidx[k];
+    asm volatile("" : "+r"(y_off[k]), "+r"(cidx[k]), "+r"(bidx[k]));  // keep them in registers: no re-derivation inside the loops
   }
+  const int row_stride = NH * P.C;
   float b2r[TAIL_MAX_OUT];
 #pragma unroll
   for (int o = 0; o < TAIL_MAX_OUT; ++o) b2r[o] = o < P.O ? __ldg(P.b2 + o) : 0.f;
@@ -156,20 +161,19 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams
 #pragma unroll
       for (int k = 0; k < L4; ++k) acc[h][k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int e0 = 0; e0 < n; e0 += G) {
+    // full batches of G entries (all gathers issued before the first FMA), then the remainder one by one
+    int e0 = 0;
+    for (; e0 + G <= n; e0 += G) {
       float4 ent[G];
       float4 u[G][NH][L4];
 #pragma unroll
       for (int t = 0; t < G; ++t) {
-        const bool live = e0 + t < n;
-        ent[t] = live ? seg[e0 + t] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int64_t joff = (int64_t)__float_as_int(ent[t].x) * NH * P.C;
+        ent[t] = seg[e0 + t];
+        const int jo = __float_as_int(ent[t].x) * row_stride;
 #pragma unroll
         for (int h = 0; h < NH; ++h)
 #pragma unroll
-          for (int k = 0; k < L4; ++k)
-            u[t][h][k] = (live && ok[k]) ? __ldg(reinterpret_cast<const float4*>(P.y + y_off[k] + joff + h * P.C))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < L4; ++k) u[t][h][k] = __ldg(reinterpret_cast<const float4*>(P.y + (y_off[k] + jo + h * P.C)));
       }
 #pragma unroll
       for (int t = 0; t < G; ++t) {
@@ -183,6 +187,26 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams
             acc[h][k].z = fmaf(pw, u[t][h][k].z, acc[h][k].z);
             acc[h][k].w = fmaf(pw, u[t][h][k].w, acc[h][k].w);
           }
+        }
+      }
+    }
+    for (; e0 < n; ++e0) {
+      const float4 ent = seg[e0];
+      const int jo = __float_as_int(ent.x) * row_stride;
+      float4 u[NH][L4];
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+#pragma unroll
+        for (int k = 0; k < L4; ++k) u[h][k] = __ldg(reinterpret_cast<const float4*>(P.y + (y_off[k] + jo + h * P.C)));
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float pw = h == 0 ? ent.z : ent.w;
+#pragma unroll
+        for (int k = 0; k < L4; ++k) {
+          acc[h][k].x = fmaf(pw, u[h][k].x, acc[h][k].x);
+          acc[h][k].y = fmaf(pw, u[h][k].y, acc[h][k].y);
+          acc[h][k].z = fmaf(pw, u[h][k].z, acc[h][k].z);
+          acc[h][k].w = fmaf(pw, u[h][k].w, acc[h][k].w);
         }
       }
     }
@@ -277,18 +301,18 @@ __device__ inline TailBwdSmem tail_bwd_carve(unsigned char* p, int cpl, int M, i
 }
 
 template <int NH, int L4>
-__device__ __forceinline__ void tail_flush_slots(const TailParams& P, const TailBwdSmem& S, const int64_t (&y_off)[L4],
+__device__ __forceinline__ void tail_flush_slots(const TailParams& P, const TailBwdSmem& S, const int (&y_off)[L4],
                                                  const bool (&ok)[L4], int tid) {
   const int used = min(S.ctl[0], P.n_slots);
   for (int sidx = 0; sidx < used; ++sidx) {
-    const int64_t joff = (int64_t)S.slot_j[sidx] * NH * P.C;
+    const int joff = (int)S.slot_j[sidx] * NH * P.C;
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
 #pragma unroll
       for (int k = 0; k < L4; ++k) {
         if (ok[k]) {
           float4* cell = S.slot_acc + ((size_t)sidx * NH + h) * P.lanes4 + tid + k * TALL_THREADS;
-          atomicAdd(reinterpret_cast<float4*>(P.d_y + y_off[k] + joff + h * P.C), *cell);
+          atomicAdd(reinterpret_cast<float4*>(P.d_y + (y_off[k] + joff + h * P.C)), *cell);
           *cell = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -301,7 +325,7 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_bwd_kernel(const TailParams
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   const TailBwdSmem S = tail_bwd_carve(tall_smem_raw, CPL, P.M, P.lanes4, NH, P.n_slots);
   constexpr int SEG = CPL * 32;
-  constexpr int G = (L4 >= 2) ? 1 : 2;
+  constexpr int G = (NH * L4 >= 8) ? 1 : (8 / (NH * L4) > 4 ? 4 : 8 / (NH * L4));  // gather batch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float period = P.period ? __ldg(P.period) : 0.f;
 
@@ -316,17 +340,20 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_bwd_kernel(const TailParams
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
 
   const int c4_per_b = P.C / 4;
-  int64_t y_off[L4];
+  int y_off[L4];
   int bidx[L4], cidx[L4];
   bool ok[L4];
 #pragma unroll
   for (int k = 0; k < L4; ++k) {
-    const int q = tid + k * TALL_THREADS;
+    int q = tid + k * TALL_THREADS;
     ok[k] = q < P.lanes4;
-    bidx[k] = ok[k] ? q / c4_per_b : 0;
-    cidx[k] = ok[k] ? (q - bidx[k] * c4_per_b) * 4 : 0;
-    y_off[k] = (int64_t)bidx[k] * P.M * NH * P.C + cidx[k];
+    q = min(q, P.lanes4 - 1);
+    bidx[k] = q / c4_per_b;
+    cidx[k] = (q - bidx[k] * c4_per_b) * 4;
+    y_off[k] = bidx[k] * P.M * NH * P.C + cidx[k];
+    asm volatile("" : "+r"(y_off[k]), "+r"(cidx[k]), "+r"(bidx[k]));
   }
+  const int row_stride = NH * P.C;
   for (int i = tid; i < P.C * (1 + P.O); i += TALL_THREADS) S.par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
   for (int j = tid; j < P.M; j += TALL_THREADS) {
     S.map[j] = -1;
@@ -433,20 +460,18 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_bwd_kernel(const TailParams
 #pragma unroll
         for (int h = 0; h < NH; ++h) acc_z[h][k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (int e0 = 0; e0 < n; e0 += G) {
+      int e0 = 0;
+      for (; e0 + G <= n; e0 += G) {
         float4 ent[G];
         float4 u[G][NH][L4];
 #pragma unroll
         for (int t = 0; t < G; ++t) {
-          const bool live = e0 + t < n;
-          ent[t] = live ? seg[e0 + t] : make_float4(0.f, 0.f, 0.f, 0.f);
-          const int64_t joff = (int64_t)__float_as_int(ent[t].x) * NH * P.C;
+          ent[t] = seg[e0 + t];
+          const int jo = __float_as_int(ent[t].x) * row_stride;
 #pragma unroll
           for (int h = 0; h < NH; ++h)
 #pragma unroll
-            for (int k = 0; k < L4; ++k)
-              u[t][h][k] = (live && ok[k]) ? __ldg(reinterpret_cast<const float4*>(P.y + y_off[k] + joff + h * P.C))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < L4; ++k) u[t][h][k] = __ldg(reinterpret_cast<const float4*>(P.y + (y_off[k] + jo + h * P.C)));
         }
 #pragma unroll
         for (int t = 0; t < G; ++t) {
@@ -465,6 +490,31 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_bwd_kernel(const TailParams
               acc_z[h][k].z = fmaf(pz, u[t][h][k].z, acc_z[h][k].z);
               acc_z[h][k].w = fmaf(pz, u[t][h][k].w, acc_z[h][k].w);
             }
+          }
+        }
+      }
+      for (; e0 < n; ++e0) {
+        const float4 ent = seg[e0];
+        const int jo = __float_as_int(ent.x) * row_stride;
+        float4 u[NH][L4];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int k = 0; k < L4; ++k) u[h][k] = __ldg(reinterpret_cast<const float4*>(P.y + (y_off[k] + jo + h * P.C)));
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float pw = h == 0 ? ent.z : ent.w;
+          const float pz = pw * (ent.y - mrow[h]);
+#pragma unroll
+          for (int k = 0; k < L4; ++k) {
+            acc_h[k].x = fmaf(pw, u[h][k].x, acc_h[k].x);
+            acc_h[k].y = fmaf(pw, u[h][k].y, acc_h[k].y);
+            acc_h[k].z = fmaf(pw, u[h][k].z, acc_h[k].z);
+            acc_h[k].w = fmaf(pw, u[h][k].w, acc_h[k].w);
+            acc_z[h][k].x = fmaf(pz, u[h][k].x, acc_z[h][k].x);
+            acc_z[h][k].y = fmaf(pz, u[h][k].y, acc_z[h][k].y);
+            acc_z[h][k].z = fmaf(pz, u[h][k].z, acc_z[h][k].z);
+            acc_z[h][k].w = fmaf(pz, u[h][k].w, acc_z[h][k].w);
           }
         }
       }
@@ -514,7 +564,6 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_bwd_kernel(const TailParams
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           const float pw = h == 0 ? ent.z : ent.w;
-          if (pw == 0.f) continue;
 #pragma unroll
           for (int k = 0; k < L4; ++k) {
             if (!ok[k]) continue;
@@ -528,7 +577,7 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_bwd_kernel(const TailParams
               cur.w += add.w;
               *cell = cur;
             } else {
-              atomicAdd(reinterpret_cast<float4*>(P.d_y + y_off[k] + (int64_t)j * NH * P.C + h * P.C), add);
+              atomicAdd(reinterpret_cast<float4*>(P.d_y + (y_off[k] + j * row_stride + h * P.C)), add);
             }
           }
         }

@@ -487,7 +487,8 @@ cudaError_t dense_launch(int geo, const pit_problem_t* p, const pit::DenseParams
 // ---------------------------------------------------------------------------------------------
 bool tail_eligible(const pit_problem_t* p, int out_dim) {
   const int c = p->dim;
-  return tall_eligible(p) && c >= 32 && c <= 512 && (c & (c - 1)) == 0 && out_dim >= 1 && out_dim <= pit::TAIL_MAX_OUT;
+  return tall_eligible(p) && c >= 32 && c <= 512 && (c & (c - 1)) == 0 && out_dim >= 1 && out_dim <= pit::TAIL_MAX_OUT &&
+         (int64_t)p->batch * p->n_in * p->n_head * c < (1ll << 31);
 }
 
 TallPlan plan_tail_fwd(const pit_problem_t* p) {
@@ -509,7 +510,7 @@ TallPlan plan_tail_bwd(const pit_problem_t* p) {
   c.cpl = cpl_of(p->n_in);
   const int budget = max_smem_optin();
   const int per_slot = p->n_head * c.lanes4 * 16;
-  c.n_slots = 48 * 1024 / per_slot;
+  c.n_slots = 32 * 1024 / per_slot;
   if (c.n_slots > 64) c.n_slots = 64;
   if (c.n_slots > p->n_in) c.n_slots = p->n_in;
   if (c.n_slots < 4) return c;
