@@ -125,6 +125,14 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams
     asm volatile("" : "+r"(y_off[k]), "+r"(cidx[k]), "+r"(bidx[k]));  // keep them in registers: no re-derivation inside the loops
   }
   const int row_stride = NH * P.C;
+  // C/4 > 32: one sample spans k_per_b consecutive register groups, folded into the first ("lead") one
+  const int k_per_b = c4_per_b > 32 ? c4_per_b / 32 : 1;
+  bool k_lead[L4], writer[L4];
+#pragma unroll
+  for (int k = 0; k < L4; ++k) {
+    k_lead[k] = (k % k_per_b) == 0;
+    writer[k] = ok[k] && k_lead[k] && (lane % segw) == 0;
+  }
   float b2r[TAIL_MAX_OUT];
 #pragma unroll
   for (int o = 0; o < TAIL_MAX_OUT; ++o) b2r[o] = o < P.O ? __ldg(P.b2 + o) : 0.f;
@@ -233,21 +241,18 @@ __global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams
       }
     }
     // reduce over the lanes (and, for C > 128, the consecutive k) that share a sample
-    const int k_per_b = c4_per_b > 32 ? c4_per_b / 32 : 1;
 #pragma unroll
     for (int oo = 0; oo < TAIL_MAX_OUT; ++oo) {
       if (oo >= P.O) break;
 #pragma unroll
       for (int k = 0; k < L4; ++k) {
+        if (!k_lead[k]) continue;  // uniform across the warp
         float v = part[oo][k];
-        if (k_per_b > 1) {
-          // C/4 > 32: one sample spans k_per_b consecutive register groups; fold them into the first one
-          if (k % k_per_b != 0) continue;
-          for (int kk = 1; kk < k_per_b && k + kk < L4; ++kk) v += part[oo][k + kk];
-        }
+#pragma unroll
+        for (int kk = 1; kk < L4; ++kk)
+          if (kk < k_per_b && k + kk < L4) v += part[oo][k + kk];
         v = seg_sum(v, segw);
-        if (ok[k] && (lane % segw) == 0 && (k_per_b == 1 || k % k_per_b == 0))
-          P.out[((int64_t)bidx[k] * P.N + r) * P.O + oo] = v + b2r[oo];
+        if (writer[k]) P.out[((int64_t)bidx[k] * P.N + r) * P.O + oo] = v + b2r[oo];
       }
     }
     __syncwarp();
