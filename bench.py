@@ -100,13 +100,18 @@ class ClockSampler:
 # algorithmic bytes of one position-attention launch
 # ----------------------------------------------------------------------------------------------
 def algorithmic_bytes(key) -> int:
+    """Q = 4*[B*M*D + B*N*H*D (+2*B*N*D concat) + sd*(N+M)*(B or 1)] for a forward stage; the
+    backward re-reads U, reads dO (and O) and writes dU.  For the fused decoder tail the figure is that of the unfused
+    stage it replaces (attention output of H*D floats per point), so `traffic` far below it is the effect of the fusion."""
     tag, _variant, batched, B, H, N, M, D, sd, concat = key
     meshes = sd * (N + M) * (B if batched else 1)
     values, outs = B * M * D, B * N * H * D
-    if tag == "fwd":
+    if tag in ("fwd", "tail_fwd"):
         words = values + outs + meshes + (2 * B * N * D if concat else 0)
     elif tag == "bwd":             # reads U and dO once (fused scale + value gradients), writes dU
         words = 2 * values + outs + meshes + (B * N * D if concat else 0)
+    elif tag == "tail_bwd":        # unfused: read dO and O (recomputed here), re-read U, write dU
+        words = 2 * values + 2 * outs + meshes
     else:                          # rowstat: coordinates in, three floats per row out
         words = meshes + 3 * N * (B if batched else 1)
     return 4 * words

@@ -86,7 +86,7 @@ __device__ __forceinline__ float seg_sum(float v, int seg) {
 // forward: one warp per row; a lane owns L4 float4 lanes (b, c..c+3) of the B*C-wide hidden vector
 // ---------------------------------------------------------------------------------------
 template <int GEO, int CPL, int NH, int L4>
-__global__ void __launch_bounds__(TALL_THREADS) tail_fwd_kernel(const TailParams P) {
+__global__ void __launch_bounds__(TALL_THREADS, 4) tail_fwd_kernel(const TailParams P) {
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   constexpr int G = (NH * L4 >= 8) ? 2 : (8 / (NH * L4));  // entries per gather batch: >= 8 independent 128-bit loads in flight
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -326,7 +326,7 @@ __device__ __forceinline__ void tail_flush_slots(const TailParams& P, const Tail
 }
 
 template <int GEO, int CPL, int NH, int L4>
-__global__ void __launch_bounds__(TALL_THREADS) tail_bwd_kernel(const TailParams P) {
+__global__ void __launch_bounds__(TALL_THREADS, (L4 == 1) ? 4 : 1) tail_bwd_kernel(const TailParams P) {
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   const TailBwdSmem S = tail_bwd_carve(tall_smem_raw, CPL, P.M, P.lanes4, NH, P.n_slots);
   constexpr int SEG = CPL * 32;

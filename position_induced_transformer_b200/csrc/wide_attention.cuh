@@ -19,7 +19,7 @@ namespace pit {
 
 constexpr int WIDE_THREADS = 128;
 constexpr int WIDE_WARPS = WIDE_THREADS / 32;
-constexpr int WIDE_CPL = 4;       // columns per lane: 128 columns per warp
+constexpr int WIDE_CPL = 2;       // columns per lane: 64 columns per warp (more warps: the row walk is latency bound)
 constexpr int WIDE_MAX_WIDTH = 32;  // B*D scalars per value row
 constexpr int WIDE_MAX_H = 2;
 
