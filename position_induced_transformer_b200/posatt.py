@@ -180,13 +180,27 @@ mesh_cache = _MeshCache()
 rowstat_cache = mesh_cache          # historical name
 
 
+_ZEROS = {}
+
+
+def _zeros(shape, device) -> torch.Tensor:
+    """Shared read-only zero tensors (row minima of global self stages): one fill per shape, not one per call."""
+    key = (tuple(shape), device)
+    z = _ZEROS.get(key)
+    if z is None:
+        if torch.cuda.is_current_stream_capturing():
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        z = _ZEROS[key] = torch.zeros(shape, dtype=torch.float32, device=device)
+    return z
+
+
 def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
     """(v_min, v_lo, v_hi, w, masked): order statistics replacing torch.quantile's row sort (uncached)."""
     masked = locality < 1.0
     k_lo, k_hi, w = _cabi.quantile_ranks(locality, st.M) if masked else (0, 0, 0.0)
     if not masked and mesh_out.data_ptr() == mesh_in.data_ptr() and mesh_out.shape == mesh_in.shape:
         # global self stage: the row minimum is d2(i, i) = 0 exactly, no statistics needed
-        zeros = torch.zeros(st.stat_shape(), dtype=torch.float32, device=st.device)
+        zeros = _zeros(st.stat_shape(), st.device)
         return zeros, zeros, zeros, w, masked
     stats = torch.empty((3,) + st.stat_shape(), dtype=torch.float32, device=st.device)
     with _timed("rowstat", st, False):
