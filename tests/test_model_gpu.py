@@ -81,15 +81,22 @@ def test_graphed_step_matches_eager(cuda_device):
         return lambda ins, tgt: w.loss(tgt, model(w.meshes[0], ins[0], w.meshes[0]))
 
     opt_g = torch.optim.Adam(w.model.parameters(), lr=1e-3, capturable=True)
-    step = GraphedTrainStep(list(w.model.parameters()), loss_of(w.model), opt_g, batches[0][0], batches[0][1], warmup=0)
+    # capture needs an eager warm-up (cuBLAS handles, Adam state): two steps on the first batch ...
+    step = GraphedTrainStep(list(w.model.parameters()), loss_of(w.model), opt_g, batches[0][0], batches[0][1], warmup=2)
     opt_e = torch.optim.Adam(ref_model.parameters(), lr=1e-3, capturable=True)
     flat = FlatGradients(ref_model.parameters(), 1)
-    # the capture itself does not run the step; both models start from the same state
-    for ins, tgt in batches:
+
+    def eager_step(ins, tgt):
         flat.zero()
-        loss_e = loss_of(ref_model)(ins, tgt)
-        loss_e.backward()
+        loss = loss_of(ref_model)(ins, tgt)
+        loss.backward()
         opt_e.step()
+        return loss
+
+    for _ in range(2):                       # ... which the eager twin takes as well
+        eager_step(*batches[0])
+    for ins, tgt in batches:
+        loss_e = eager_step(ins, tgt)
         loss_g = step(ins, tgt)
         assert abs(float(loss_g) - float(loss_e)) <= 1e-4 * abs(float(loss_e))
     for a, b in zip(w.model.parameters(), ref_model.parameters()):
