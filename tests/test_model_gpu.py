@@ -81,10 +81,10 @@ def test_graphed_step_matches_eager(cuda_device):
         return lambda ins, tgt: w.loss(tgt, model(w.meshes[0], ins[0], w.meshes[0]))
 
     # plain SGD: Adam's sign-like first steps would amplify the 1e-7 summation-order noise of the atomics
-    opt_g = torch.optim.SGD(w.model.parameters(), lr=1e-2)
+    opt_g = torch.optim.SGD(w.model.parameters(), lr=1e-5)
     # capture needs an eager warm-up (cuBLAS handles, allocator pools): two steps on the first batch ...
     step = GraphedTrainStep(list(w.model.parameters()), loss_of(w.model), opt_g, batches[0][0], batches[0][1], warmup=2)
-    opt_e = torch.optim.SGD(ref_model.parameters(), lr=1e-2)
+    opt_e = torch.optim.SGD(ref_model.parameters(), lr=1e-5)
     flat = FlatGradients(ref_model.parameters(), 1)
 
     def eager_step(ins, tgt):
