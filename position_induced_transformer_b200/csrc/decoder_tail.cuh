@@ -275,10 +275,10 @@ struct TailBwdSmem {
   float* par;        // [C + O*C]: b1 then W2
 };
 
-__host__ __device__ inline size_t tail_bwd_smem_bytes(int cpl, int M, int lanes4, int nh, int n_slots) {
+__host__ __device__ inline size_t tail_bwd_smem_bytes(int cpl, int M, int lanes4, int nh, int n_slots, int C, int O) {
   return (size_t)TALL_WARPS * cpl * 32 * 16 + tall_align((size_t)n_slots * nh * lanes4 * 16) + tall_align(TALL_WARPS * 2 * 4) +
          tall_align(TALL_WARPS * 4) + tall_align((size_t)M * 2) + tall_align((size_t)n_slots * 2 + 2) + tall_align(M) + 16 + 64 +
-         (size_t)512 * (1 + TAIL_MAX_OUT) * 4;
+         tall_align((size_t)C * (1 + O) * 4);
 }
 
 __device__ inline TailBwdSmem tail_bwd_carve(unsigned char* p, int cpl, int M, int lanes4, int nh, int n_slots) {

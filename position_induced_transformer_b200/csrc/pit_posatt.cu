@@ -500,7 +500,7 @@ TallPlan plan_tail_fwd(const pit_problem_t* p) {
   return c;
 }
 
-TallPlan plan_tail_bwd(const pit_problem_t* p) {
+TallPlan plan_tail_bwd(const pit_problem_t* p, int out_dim) {
   TallPlan c{};
   if (!tall_eligible(p)) return c;
   c.lanes4 = p->batch * p->dim / 4;
@@ -514,7 +514,7 @@ TallPlan plan_tail_bwd(const pit_problem_t* p) {
   if (c.n_slots > 64) c.n_slots = 64;
   if (c.n_slots > p->n_in) c.n_slots = p->n_in;
   if (c.n_slots < 4) return c;
-  c.smem = pit::tail_bwd_smem_bytes(c.cpl, p->n_in, c.lanes4, p->n_head, c.n_slots);
+  c.smem = pit::tail_bwd_smem_bytes(c.cpl, p->n_in, c.lanes4, p->n_head, c.n_slots, p->dim, out_dim);
   if (c.smem > (size_t)budget - 1024) return c;
   int per_sm = (int)((size_t)budget / (c.smem + 1024));
   if (per_sm > 8) per_sm = 8;
@@ -890,7 +890,7 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
 int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim) {
   if (check_problem(p) != PIT_OK) return 0;
   if (!tail_eligible(p, out_dim)) return 0;
-  return plan_tail_fwd(p).ok && plan_tail_bwd(p).ok ? 1 : 0;
+  return plan_tail_fwd(p).ok && plan_tail_bwd(p, out_dim).ok ? 1 : 0;
 }
 
 int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
@@ -923,7 +923,7 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   if (!tail_eligible(p, out_dim)) return fail(PIT_ERR_ARG, "decoder tail: unsupported configuration (see pit_decoder_tail_supported)");
   if (!aligned16(y) || !aligned16(b1) || !aligned16(w2) || !aligned16(d_y) || !aligned16(d_b1) || !aligned16(d_w2))
     return fail(PIT_ERR_ARG, "decoder tail: y, b1, w2 and their gradients must be 16-byte aligned");
-  const TallPlan plan = plan_tail_bwd(p);
+  const TallPlan plan = plan_tail_bwd(p, out_dim);
   if (!plan.ok) return fail(PIT_ERR_ARG, "decoder tail: no launch plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
