@@ -2,11 +2,13 @@
 
     python -m position_induced_transformer_b200.build [--force] [--verbose]
 
-The library is plain CUDA C++ behind a C ABI (include/pit_posatt.h): no torch headers, so it
-compiles in seconds with nvcc alone and cross-compiles without a GPU.
+The library is plain CUDA C++ behind a C ABI (include/pit_posatt.h): no torch headers.  Every kernel family has
+its own translation unit (csrc/tu_*.cu) so that the template instantiations compile in parallel; objects go to
+csrc/_obj/ and are linked into one shared library.  nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
 
+import concurrent.futures
 import os
 import shutil
 import subprocess
@@ -14,12 +16,10 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG, "libpit_posatt.so")
-SOURCES = [os.path.join(CSRC, "pit_posatt.cu")]
-NVCC_FLAGS = [
-    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+HEADER = os.path.join(os.path.dirname(PKG), "include", "pit_posatt.h")
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:
@@ -29,24 +29,50 @@ def _nvcc() -> str:
     return exe
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [HEADER]
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    built = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(PKG), "include", "pit_posatt.h")]
+    built = os.path.getmtime(target)
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if missing or older than its sources; returns its path."""
-    if not force and not _stale():
-        return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *SOURCES]
+def _compile(src: str, verbose: bool) -> str:
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", src, "-o", obj]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile whatever is missing or older than its sources and link; returns the library path."""
+    deps = _deps()
+    if not force and not _stale(LIB, deps):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [d for d in deps if not d.endswith(".cu")]
+    todo = [s for s in _sources()
+            if force or _stale(os.path.join(OBJ, os.path.basename(s)[:-3] + ".o"), [s, *headers])]
+    workers = max(1, min(len(todo), os.cpu_count() or 1))
+    if todo:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=workers) as pool:
+            list(pool.map(lambda s: _compile(s, verbose), todo))
+    objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in _sources()]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     return LIB
 
 

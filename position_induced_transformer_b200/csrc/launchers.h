@@ -1,0 +1,51 @@
+// Host-side launch layer: one function per kernel family, each defined in its own translation unit so that the
+// template instantiations compile in parallel (see build.py).  The C ABI (pit_posatt.cu) only plans and calls these.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "decoder_tail.cuh"
+#include "dense_attention.cuh"
+#include "local_attention.cuh"
+#include "rowstat.cuh"
+#include "tall_attention.cuh"
+#include "wide_attention.cuh"
+
+namespace pit {
+namespace launch {
+
+struct TallPlan {
+  bool ok;
+  int cpl, l4, lanes4, chunks, rows_per_unit, grid, n_slots;
+  size_t smem;
+};
+
+struct WidePlan {
+  bool ok;
+  int grid;
+  size_t smem;
+};
+
+// tu_local.cu
+cudaError_t rowstat(int geo, const RowstatParams& R, cudaStream_t st);
+cudaError_t local_forward(int geo, int vec, int a, dim3 grid, const AttnParams& P, cudaStream_t st);
+cudaError_t local_dscale(int geo, int vec, int a, dim3 grid, const AttnParams& P, cudaStream_t st);
+cudaError_t local_dvalues(int geo, int vec, int a, dim3 grid, const AttnParams& P, cudaStream_t st);
+cudaError_t local_forward_finalize(int64_t total, const AttnParams& P, cudaStream_t st);
+cudaError_t local_dscale_finalize(int64_t items, const AttnParams& P, float* rows, cudaStream_t st);
+cudaError_t reduce_scale_rows(const float* rows, int64_t n_rows, int H, float* d_scale, cudaStream_t st);
+// tu_tall_fwd.cu / tu_tall_bwd.cu
+cudaError_t tall_forward(int geo, const TallPlan& plan, const TallParams& P, cudaStream_t st);
+cudaError_t tall_backward(int geo, const TallPlan& plan, const TallParams& P, bool with_values, cudaStream_t st);
+// tu_tail_fwd.cu / tu_tail_bwd.cu
+cudaError_t tail_forward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
+cudaError_t tail_backward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
+// tu_wide.cu
+int wide_pad(int width);
+cudaError_t wide_forward(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
+cudaError_t wide_dscale(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
+// tu_dense.cu  (mode: DENSE_FWD / DENSE_DSCALE / DENSE_DVALUES; nv: 64, 128 or 256 value columns per tile)
+cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cudaStream_t st);
+
+}  // namespace launch
+}  // namespace pit

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) posatt_fwd_kernel(const 
 }
 
 // Split forward: out = partial / rowsum.  One thread per (item, element).
-__global__ void posatt_fwd_finalize_kernel(const AttnParams P) {
+static __global__ void posatt_fwd_finalize_kernel(const AttnParams P) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rows_total = (P.mesh_batched ? P.B : 1) * P.N;
   const int64_t total = (int64_t)rows_total * P.H * P.width;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) posatt_dscale_kernel(con
 }
 
 // rows[item] = -(A - (m/l) Bq) / l   with item = row * H + h (summed per head by the host-side reduction)
-__global__ void posatt_dscale_finalize_kernel(const AttnParams P, float* __restrict__ rows) {
+static __global__ void posatt_dscale_finalize_kernel(const AttnParams P, float* __restrict__ rows) {
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rows_total = (P.mesh_batched ? P.B : 1) * P.N;
   if (item >= (int64_t)rows_total * P.H) return;

@@ -11,14 +11,13 @@
 #include <atomic>
 #include <type_traits>
 
-#include "decoder_tail.cuh"
-#include "dense_attention.cuh"
-#include "tall_attention.cuh"
-#include "wide_attention.cuh"
-#include "local_attention.cuh"
-#include "rowstat.cuh"
+#include "launchers.h"
 
 namespace {
+
+using pit::launch::TallPlan;
+using pit::launch::WidePlan;
+namespace launch = pit::launch;
 
 thread_local char g_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
@@ -144,37 +143,10 @@ int check_stat(const pit_problem_t* p, const pit_rowstat_t* st, const float* per
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-// Dispatch a <GEO, VEC, A> kernel template.
-#define PIT_DISPATCH_A(KERNEL, GEO, VEC, a, ...)                       \
-  switch (a) {                                                          \
-    case 1: KERNEL<GEO, VEC, 1> __VA_ARGS__; break;                     \
-    case 2: KERNEL<GEO, VEC, 2> __VA_ARGS__; break;                     \
-    default: KERNEL<GEO, VEC, 4> __VA_ARGS__; break;                    \
-  }
-#define PIT_DISPATCH_VEC(KERNEL, GEO, vec, a, ...)                      \
-  if ((vec) == 4) {                                                     \
-    PIT_DISPATCH_A(KERNEL, GEO, 4, a, __VA_ARGS__)                      \
-  } else {                                                              \
-    PIT_DISPATCH_A(KERNEL, GEO, 1, a, __VA_ARGS__)                      \
-  }
-#define PIT_DISPATCH(KERNEL, geo, vec, a, ...)                                              \
-  switch (geo) {                                                                             \
-    case pit::GEO_EUCLID1: PIT_DISPATCH_VEC(KERNEL, pit::GEO_EUCLID1, vec, a, __VA_ARGS__) break;     \
-    case pit::GEO_EUCLID2: PIT_DISPATCH_VEC(KERNEL, pit::GEO_EUCLID2, vec, a, __VA_ARGS__) break;     \
-    case pit::GEO_PERIODIC1: PIT_DISPATCH_VEC(KERNEL, pit::GEO_PERIODIC1, vec, a, __VA_ARGS__) break; \
-    default: PIT_DISPATCH_VEC(KERNEL, pit::GEO_PERIODIC2, vec, a, __VA_ARGS__) break;                 \
-  }
-
 
 // ---------------------------------------------------------------------------------------------
 // "tall" kernels (shared meshes, M <= 1024, H <= 2): eligibility, launch shape, dispatch
 // ---------------------------------------------------------------------------------------------
-struct TallPlan {
-  bool ok;
-  int cpl, l4, lanes4, chunks, rows_per_unit, grid, n_slots;
-  size_t smem;
-};
-
 int max_smem_optin() {
   static int cached = 0;
   if (cached == 0) {
@@ -192,7 +164,7 @@ bool tall_eligible(const pit_problem_t* p) {
   return !p->mesh_batched && p->n_in <= pit::TALL_MAX_M && p->dim % 4 == 0 && p->n_head <= pit::TALL_MAX_H;
 }
 
-int cpl_of(int m) { return m <= 128 ? 4 : (m <= 256 ? 8 : (m <= 512 ? 16 : 32)); }
+int cpl_of(int m) { return m <= 256 ? 8 : 32; }  // instantiated column-per-lane counts
 
 // forward: one warp per row, 32*l4 float4 lanes per warp pass, `chunks` passes over blockIdx.y
 TallPlan plan_tall_fwd(const pit_problem_t* p) {
@@ -271,69 +243,9 @@ pit::TallParams tall_params(const pit_problem_t* p, const TallPlan& c, const flo
   return P;
 }
 
-template <typename K>
-cudaError_t tall_launch(K kernel, const TallPlan& c, const pit::TallParams& P, cudaStream_t st) {
-  if (c.smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-    if (e != cudaSuccess) return e;
-  }
-  kernel<<<dim3(c.grid, c.chunks), pit::TALL_THREADS, c.smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-template <int V>
-using Int = std::integral_constant<int, V>;
-
-// Calls f(Int<GEO>, Int<CPL>, Int<NH>, Int<L4>) for the runtime values.
-template <typename G, typename C, typename H, typename F>
-cudaError_t with_l4(G g, C c, H h, int l4, F&& f) {
-  if (l4 == 1) return f(g, c, h, Int<1>{});
-  if (l4 == 2) return f(g, c, h, Int<2>{});
-  return f(g, c, h, Int<4>{});
-}
-template <typename G, typename C, typename F>
-cudaError_t with_heads(G g, C c, int nh, int l4, F&& f) {
-  if (nh == 1) return with_l4(g, c, Int<1>{}, l4, f);
-  return with_l4(g, c, Int<2>{}, l4, f);
-}
-template <typename G, typename F>
-cudaError_t with_cpl(G g, int cpl, int nh, int l4, F&& f) {
-  if (cpl == 4) return with_heads(g, Int<4>{}, nh, l4, f);
-  if (cpl == 8) return with_heads(g, Int<8>{}, nh, l4, f);
-  if (cpl == 16) return with_heads(g, Int<16>{}, nh, l4, f);
-  return with_heads(g, Int<32>{}, nh, l4, f);
-}
-template <typename F>
-cudaError_t with_geo(int geo, int cpl, int nh, int l4, F&& f) {
-  if (geo == pit::GEO_EUCLID1) return with_cpl(Int<pit::GEO_EUCLID1>{}, cpl, nh, l4, f);
-  if (geo == pit::GEO_EUCLID2) return with_cpl(Int<pit::GEO_EUCLID2>{}, cpl, nh, l4, f);
-  if (geo == pit::GEO_PERIODIC1) return with_cpl(Int<pit::GEO_PERIODIC1>{}, cpl, nh, l4, f);
-  return with_cpl(Int<pit::GEO_PERIODIC2>{}, cpl, nh, l4, f);
-}
-
-cudaError_t tall_forward(int geo, const TallPlan& plan, const pit::TallParams& P, cudaStream_t st) {
-  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
-    return tall_launch(pit::tall_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value, decltype(l)::value>, plan, P, st);
-  });
-}
-cudaError_t tall_backward(int geo, const TallPlan& plan, const pit::TallParams& P, bool with_values, cudaStream_t st) {
-  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
-    constexpr int G = decltype(g)::value, C = decltype(c)::value, NH = decltype(h)::value, L = decltype(l)::value;
-    return with_values ? tall_launch(pit::tall_bwd_kernel<G, C, NH, L, true>, plan, P, st)
-                       : tall_launch(pit::tall_bwd_kernel<G, C, NH, L, false>, plan, P, st);
-  });
-}
-
-
 // ---------------------------------------------------------------------------------------------
 // "wide" kernels (shared meshes, few rows, huge column set, narrow values): the local encoder
 // ---------------------------------------------------------------------------------------------
-struct WidePlan {
-  bool ok;
-  int grid;
-  size_t smem;
-};
-
 WidePlan plan_wide(const pit_problem_t* p, const pit_rowstat_t* st) {
   WidePlan w{};
   const int width = p->batch * p->dim;
@@ -370,47 +282,6 @@ pit::WideParams wide_params(const pit_problem_t* p, const float* mesh_out, const
   P.width = p->batch * p->dim;
   return P;
 }
-
-template <typename K>
-cudaError_t wide_launch(K kernel, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
-  if (w.smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
-    if (e != cudaSuccess) return e;
-  }
-  kernel<<<w.grid, pit::WIDE_THREADS, w.smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-int wide_pad(int width) { return width <= 8 ? 8 : (width <= 16 ? 16 : (width <= 24 ? 24 : 32)); }
-
-template <typename F>
-cudaError_t with_geo_heads_pad(int geo, int nh, int wpad, F&& f) {
-  auto pad = [&](auto g, auto h) {
-    if (wpad == 8) return f(g, h, Int<8>{});
-    if (wpad == 16) return f(g, h, Int<16>{});
-    if (wpad == 24) return f(g, h, Int<24>{});
-    return f(g, h, Int<32>{});
-  };
-  auto heads = [&](auto g) { return nh == 1 ? pad(g, Int<1>{}) : pad(g, Int<2>{}); };
-  if (geo == pit::GEO_EUCLID1) return heads(Int<pit::GEO_EUCLID1>{});
-  if (geo == pit::GEO_EUCLID2) return heads(Int<pit::GEO_EUCLID2>{});
-  if (geo == pit::GEO_PERIODIC1) return heads(Int<pit::GEO_PERIODIC1>{});
-  return heads(Int<pit::GEO_PERIODIC2>{});
-}
-
-cudaError_t wide_forward(int geo, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
-  return with_geo_heads_pad(geo, P.H, wide_pad(P.width), [&](auto g, auto h, auto wp) {
-    return wide_launch(pit::wide_fwd_kernel<decltype(g)::value, decltype(h)::value, decltype(wp)::value>, w, P, st);
-  });
-}
-cudaError_t wide_dscale(int geo, const WidePlan& w, const pit::WideParams& P, cudaStream_t st) {
-  WidePlan wb = w;  // the backward also keeps the upstream-gradient rows in shared memory
-  wb.smem += (size_t)P.N * P.H * wide_pad(P.width) * sizeof(float);
-  return with_geo_heads_pad(geo, P.H, wide_pad(P.width), [&](auto g, auto h, auto wp) {
-    return wide_launch(pit::wide_dscale_kernel<decltype(g)::value, decltype(h)::value, decltype(wp)::value>, wb, P, st);
-  });
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // dense (global) stages on tcgen05: eligibility, tile width, dispatch
@@ -450,37 +321,15 @@ pit::DenseParams dense_params(const pit_problem_t* p, const float* mesh_out, con
   return P;
 }
 
-template <int GEO, int MODE, int NV>
-cudaError_t dense_launch_one(const pit::DenseParams& P, dim3 grid, cudaStream_t st) {
-  auto kernel = pit::dense_attention_kernel<GEO, MODE, NV>;
-  constexpr int smem = pit::DenseSmem<MODE, NV>::TOTAL;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  kernel<<<grid, pit::DENSE_THREADS, smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-template <int MODE>
-cudaError_t dense_launch(int geo, const pit_problem_t* p, const pit::DenseParams& P, cudaStream_t st) {
+cudaError_t dense_launch(int mode, int geo, const pit_problem_t* p, const pit::DenseParams& P, cudaStream_t st) {
   const int row_tiles = (P.n_own + pit::DENSE_ROWS - 1) / pit::DENSE_ROWS;
-  const int z = MODE == pit::DENSE_DVALUES ? (p->mesh_batched ? p->batch : 1) : p->n_head * (p->mesh_batched ? p->batch : 1);
+  const int z = mode == pit::DENSE_DVALUES ? (p->mesh_batched ? p->batch : 1) : p->n_head * (p->mesh_batched ? p->batch : 1);
   // widest tile that still gives the GPU enough CTAs; the scale-gradient mode holds two accumulators (max 128 columns each)
-  int nv = MODE == pit::DENSE_DSCALE ? 128 : 256;
+  int nv = mode == pit::DENSE_DSCALE ? 128 : 256;
   while (nv > 64 && ((int64_t)row_tiles * z * ((P.width + nv - 1) / nv) < sm_count() || nv / 2 >= P.width)) nv /= 2;
   const dim3 grid(row_tiles, (P.width + nv - 1) / nv, z);
-  auto pick = [&](auto g) -> cudaError_t {
-    constexpr int G = decltype(g)::value;
-    if (nv == 64) return dense_launch_one<G, MODE, 64>(P, grid, st);
-    if (nv == 128) return dense_launch_one<G, MODE, 128>(P, grid, st);
-    if constexpr (MODE != pit::DENSE_DSCALE) return dense_launch_one<G, MODE, 256>(P, grid, st);
-    return cudaErrorInvalidValue;
-  };
-  if (geo == pit::GEO_EUCLID1) return pick(Int<pit::GEO_EUCLID1>{});
-  if (geo == pit::GEO_EUCLID2) return pick(Int<pit::GEO_EUCLID2>{});
-  if (geo == pit::GEO_PERIODIC1) return pick(Int<pit::GEO_PERIODIC1>{});
-  return pick(Int<pit::GEO_PERIODIC2>{});
+  return launch::dense(mode, geo, nv, grid, P, st);
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // fused decoder tail (shared meshes, M <= 1024, H <= 2, hidden width a power of two in [32, 512], out_dim <= 4)
@@ -559,43 +408,6 @@ pit::TailParams tail_params(const pit_problem_t* p, const TallPlan& c, const flo
   return P;
 }
 
-template <typename K>
-cudaError_t tail_launch(K kernel, const TallPlan& c, const pit::TailParams& P, cudaStream_t st) {
-  if (c.smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-    if (e != cudaSuccess) return e;
-  }
-  kernel<<<dim3(c.grid, c.chunks), pit::TALL_THREADS, c.smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-cudaError_t tail_forward(int geo, const TallPlan& plan, const pit::TailParams& P, cudaStream_t st) {
-  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
-    return tail_launch(pit::tail_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value, decltype(l)::value>, plan, P, st);
-  });
-}
-cudaError_t tail_backward(int geo, const TallPlan& plan, const pit::TailParams& P, cudaStream_t st) {
-  return with_geo(geo, plan.cpl, P.H, plan.l4, [&](auto g, auto c, auto h, auto l) {
-    return tail_launch(pit::tail_bwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value, decltype(l)::value>, plan, P, st);
-  });
-}
-
-// Sum of the per-row scale-gradient terms of one head (generic path): d_scale[h] = sum_rows rows[row*H + h].
-__global__ void reduce_scale_rows_kernel(const float* __restrict__ rows, int64_t n_rows, int H, float* __restrict__ d_scale) {
-  __shared__ float red[32];
-  const int h = blockIdx.x;
-  float acc = 0.f;
-  for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) acc += rows[r * H + h];
-  acc = pit::warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    d_scale[h] = t;
-  }
-}
-
 }  // namespace
 
 extern "C" {
@@ -648,23 +460,8 @@ int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh
   R.k_lo = k_lo;
   R.k_hi = k_hi;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int geo = geo_of(p);
-#define ROWSTAT_WARP(GEO, Rn) pit::rowstat_warp_kernel<GEO, Rn><<<(R.rows_total + 3) / 4, 128, 0, st>>>(R)
-#define ROWSTAT_GEO(GEO)                                                               \
-  if (R.M <= 128) ROWSTAT_WARP(GEO, 4);                                                \
-  else if (R.M <= 256) ROWSTAT_WARP(GEO, 8);                                           \
-  else if (R.M <= 512) ROWSTAT_WARP(GEO, 16);                                          \
-  else if (R.M <= 1024) ROWSTAT_WARP(GEO, 32);                                         \
-  else pit::rowstat_block_kernel<GEO><<<R.rows_total, pit::ROWSTAT_BLOCK, 0, st>>>(R)
-  switch (geo) {
-    case pit::GEO_EUCLID1: ROWSTAT_GEO(pit::GEO_EUCLID1); break;
-    case pit::GEO_EUCLID2: ROWSTAT_GEO(pit::GEO_EUCLID2); break;
-    case pit::GEO_PERIODIC1: ROWSTAT_GEO(pit::GEO_PERIODIC1); break;
-    default: ROWSTAT_GEO(pit::GEO_PERIODIC2); break;
-  }
-#undef ROWSTAT_GEO
-#undef ROWSTAT_WARP
-  PIT_LAUNCHED();
+  PIT_CUDA(launch::rowstat(geo_of(p), R, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }
 
@@ -696,7 +493,7 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     Dn.ld_out = ld_out;
     Dn.col_off = col_off;
     Dn.rowsum_out = rowsum;
-    PIT_CUDA(dense_launch<pit::DENSE_FWD>(geo_of(p), p, Dn, st));
+    PIT_CUDA(dense_launch(pit::DENSE_FWD, geo_of(p), p, Dn, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return PIT_OK;
   }
@@ -707,7 +504,7 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     C.ld_out = ld_out;
     C.col_off = col_off;
     C.rowsum = rowsum;
-    PIT_CUDA(tall_forward(geo_of(p), plan, C, st));
+    PIT_CUDA(launch::tall_forward(geo_of(p), plan, C, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return PIT_OK;
   }
@@ -727,11 +524,11 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     pit::WideParams W = wide_params(p, mesh_out, mesh_in, period, values, scale, stat);
     W.partial = P.partial;
     W.rowsum = rowsum;
-    PIT_CUDA(wide_forward(geo_of(p), wide, W, st));
+    PIT_CUDA(launch::wide_forward(geo_of(p), wide, W, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const int64_t total = s.items * s.width;
-    pit::posatt_fwd_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P);
-    PIT_LAUNCHED();
+    PIT_CUDA(launch::local_forward_finalize(total, P, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return PIT_OK;
   }
   if (s.n_split > 1) {
@@ -742,13 +539,12 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     PIT_CUDA(cudaMemsetAsync(rowsum, 0, (size_t)s.items * sizeof(float), st));
   }
   const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
-  const dim3 block(pit::WARPS_PER_BLOCK * 32);
-  PIT_DISPATCH(pit::posatt_fwd_kernel, geo_of(p), s.vec, s.a, <<<grid, block, 0, st>>>(P));
-  PIT_LAUNCHED();
+  PIT_CUDA(launch::local_forward(geo_of(p), s.vec, s.a, grid, P, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   if (s.n_split > 1) {
     const int64_t total = s.items * s.width;
-    pit::posatt_fwd_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P);
-    PIT_LAUNCHED();
+    PIT_CUDA(launch::local_forward_finalize(total, P, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   return PIT_OK;
 }
@@ -787,7 +583,7 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
       Dn.col_off = col_off;
       Dn.d_scale = d_scale;
       PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
-      PIT_CUDA(dense_launch<pit::DENSE_DSCALE>(geo, p, Dn, st));
+      PIT_CUDA(dense_launch(pit::DENSE_DSCALE, geo, p, Dn, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
       scale_done = true;
     }
@@ -804,7 +600,7 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
       Dn.col_off = col_off;
       Dn.d_values = d_values;
       Dn.add_concat = accumulate_concat;
-      PIT_CUDA(dense_launch<pit::DENSE_DVALUES>(geo, p, Dn, st));
+      PIT_CUDA(dense_launch(pit::DENSE_DVALUES, geo, p, Dn, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
       values_done = true;
     }
@@ -822,7 +618,7 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
       C.d_scale = d_scale;
       if (d_scale) PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
       if (fuse_values) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
-      PIT_CUDA(tall_backward(geo, plan, C, fuse_values, st));
+      PIT_CUDA(launch::tall_backward(geo, plan, C, fuse_values, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
       scale_done = true;
       if (fuse_values) values_done = true;
@@ -836,7 +632,6 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   P.col_off = col_off;
   P.d_values = d_values;
   P.add_concat = accumulate_concat;
-  const dim3 block(pit::WARPS_PER_BLOCK * 32);
 
   if (!scale_done) {
     Shape s = make_shape(p, rows_total * p->n_head, p->n_in, true);
@@ -853,17 +648,16 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
       W.ld_out = ld_out;
       W.col_off = col_off;
       W.dscale_terms = P.dscale_terms;
-      PIT_CUDA(wide_dscale(geo, wide, W, st));
+      PIT_CUDA(launch::wide_dscale(geo, wide, W, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
       const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
-      PIT_DISPATCH(pit::posatt_dscale_kernel, geo, s.vec, s.a, <<<grid, block, 0, st>>>(P));
-      PIT_LAUNCHED();
+      PIT_CUDA(launch::local_dscale(geo, s.vec, s.a, grid, P, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    pit::posatt_dscale_finalize_kernel<<<(unsigned)((s.items + 255) / 256), 256, 0, st>>>(P, rows);
-    PIT_LAUNCHED();
-    reduce_scale_rows_kernel<<<p->n_head, 512, 0, st>>>(rows, rows_total, p->n_head, d_scale);
-    PIT_LAUNCHED();
+    PIT_CUDA(launch::local_dscale_finalize(s.items, P, rows, st));
+    PIT_CUDA(launch::reduce_scale_rows(rows, rows_total, p->n_head, d_scale, st));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
   }
   if (!values_done) {
     Shape s = make_shape(p, cols_total, p->n_out * p->n_head, true);
@@ -880,8 +674,8 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
     P.split_len = s.split_len;
     if (s.n_split > 1) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
     const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
-    PIT_DISPATCH(pit::posatt_dvalues_kernel, geo, s.vec, s.a, <<<grid, block, 0, st>>>(P));
-    PIT_LAUNCHED();
+    PIT_CUDA(launch::local_dvalues(geo, s.vec, s.a, grid, P, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   return PIT_OK;
 }
@@ -907,7 +701,7 @@ int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, cons
   pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
   P.out = out;
   P.rowsum = rowsum;
-  PIT_CUDA(tail_forward(geo_of(p), plan, P, st));
+  PIT_CUDA(launch::tail_forward(geo_of(p), plan, P, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }
@@ -940,7 +734,7 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   PIT_CUDA(cudaMemsetAsync(d_b1, 0, c * sizeof(float), st));
   PIT_CUDA(cudaMemsetAsync(d_w2, 0, (size_t)out_dim * c * sizeof(float), st));
   PIT_CUDA(cudaMemsetAsync(d_b2, 0, (size_t)out_dim * sizeof(float), st));
-  PIT_CUDA(tail_backward(geo_of(p), plan, P, st));
+  PIT_CUDA(launch::tail_backward(geo_of(p), plan, P, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }
