@@ -276,27 +276,32 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     if (MODE != DENSE_DVALUES) own_vmin = __ldg(P.v_min + (int64_t)sample * P.N + (own_ok ? own : 0));
     float lsum = 0.f, msum = 0.f;
 
+    // The reduced point of the NEXT K block is fetched while the current block is computed, so the global-load
+    // latency (the longest dependency of a K block at small problem sizes) is off the critical path.
+    auto fetch = [&](int kb) -> float4 {
+      const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : h_fixed;
+      const int k = (kb % kb_per_head) * DENSE_KB + lane;
+      const bool ok = kb < n_kb && k < P.n_red;
+      const Point<GEO> q = load_point<GEO>(mesh_red, ok ? k : 0, P.sd);
+      float bias = 0.f, post = 1.f;
+      if (MODE == DENSE_DVALUES && ok) {
+        bias = __ldg(P.v_min + (int64_t)sample * P.N + k) * (__ldg(P.scale + h) * LOG2E);
+        post = 1.f / __ldg(P.rowsum + ((int64_t)sample * P.H + h) * P.N + k);
+      }
+      return make_float4(ok ? q.x : INFINITY, q.y, bias, post);  // points past the end sit at infinity: weight exp2(-inf) = 0
+    };
+    float4 next_pt = fetch(0);
+
     for (int kb = 0; kb < n_kb; ++kb) {
       const int s = kb % DENSE_STAGES;
       const uint32_t use = kb / DENSE_STAGES;
       const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : h_fixed;
-      const int k0 = (kb % kb_per_head) * DENSE_KB;
       const float sc2 = __ldg(P.scale + h) * LOG2E;
-      // the 32 reduced points of this block (per-warp copy: no block-level sync needed): (x, y, shift*sc2, post).
-      // Points past the end sit at infinity, so their weight is exp2(-inf) = 0 without any predicate.
-      {
-        const int k = k0 + lane;
-        const bool ok = k < P.n_red;
-        const Point<GEO> q = load_point<GEO>(mesh_red, ok ? k : 0, P.sd);
-        float bias = 0.f, post = 1.f;
-        if (MODE == DENSE_DVALUES && ok) {
-          bias = __ldg(P.v_min + (int64_t)sample * P.N + k) * sc2;
-          post = 1.f / __ldg(P.rowsum + ((int64_t)sample * P.H + h) * P.N + k);
-        }
-        __syncwarp();
-        my_pts[lane] = make_float4(ok ? q.x : INFINITY, q.y, bias, post);
-        __syncwarp();
-      }
+      // the 32 reduced points of this block (per-warp copy: no block-level sync needed): (x, y, shift*sc2, post)
+      __syncwarp();
+      my_pts[lane] = next_pt;
+      __syncwarp();
+      next_pt = fetch(kb + 1);
       const float my_bias = own_vmin * sc2;
       mbar_wait(&empty_bar[s], (use & 1) ^ 1);
       unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES;
