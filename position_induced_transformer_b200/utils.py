@@ -3,10 +3,14 @@
 Same names and call semantics (``RelLpNorm(out_dim, p)(true, pred)`` etc., utils.py:6-98); these sit
 outside the position-attention hot path and are ordinary torch code.
 """
+import operator
+from functools import reduce
+
 import torch
 import torch.nn.functional as F
 
-__all__ = ["PixelWiseNormalization", "count_params", "RelMaxNorm", "RelLpNorm"]
+# the reference module has no __all__, so `from utils import *` also hands out its imports (utils.py:1-4)
+__all__ = ["PixelWiseNormalization", "count_params", "RelMaxNorm", "RelLpNorm", "operator", "reduce", "torch", "F"]
 
 
 def count_params(model) -> int:

@@ -103,3 +103,23 @@ def test_losses_match_oracle_formula():
     x = torch.rand(2, 8, 8, 1, generator=g)
     assert torch.allclose(norm.denormalize(norm.normalize(x)), x, atol=1e-6)
     assert norm.normalize(torch.rand(2, 16, 16, 1, generator=g)).shape == (2, 16, 16, 1)
+
+
+def test_star_import_surface_covers_the_reference():
+    """`from pit import *; from utils import *` (what every train_*.py does) yields at least the reference's names."""
+    import importlib.util
+    import subprocess
+    import sys
+    if not os.path.exists("/root/reference/pit.py"):
+        pytest.skip("reference sources only exist in the build container")
+    code = ("ns = {}\nexec('from pit import *\\nfrom utils import *', ns)\n"
+            "print(' '.join(sorted(k for k in ns if not k.startswith('_'))))")
+    out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", env={**os.environ, "PYTHONPATH": ROOT},
+                         capture_output=True, text=True, check=True).stdout.split()
+    want = set()
+    for name in ("pit", "utils"):
+        spec = importlib.util.spec_from_file_location("ref_surface_" + name, f"/root/reference/{name}.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        want |= {k for k in vars(mod) if not k.startswith("_")}
+    assert want <= set(out), sorted(want - set(out))
