@@ -561,45 +561,28 @@ __global__ void __launch_bounds__(TALL_THREADS, (L4 == 1) ? 4 : 1) tail_bwd_kern
         for (int h = 0; h < NH; ++h)
           ds_head[h] += g1[k].x * acc_z[h][k].x + g1[k].y * acc_z[h][k].y + g1[k].z * acc_z[h][k].z + g1[k].w * acc_z[h][k].w;
       }
-      // pass B: dY[b, j, h, :] += P^_hj g1.  The columns of one row are distinct, hence so are the slot cells of a
-      // batch: all cells are loaded first, updated, then stored (the compiler alone must assume they may alias and
-      // would serialise load -> add -> store per cell).  Unbound columns (slot set exhausted) use vector REDs.
-      constexpr int GB = (NH * L4 >= 8) ? 1 : ((8 / (NH * L4)) > 4 ? 4 : 8 / (NH * L4));
-      for (int e0 = 0; e0 < n; e0 += GB) {
-        float4 ent[GB];
-        int sidx[GB];
-        float4 cur[GB][NH][L4];
+      // pass B: dY[b, j, h, :] += P^_hj g1
+      for (int e = 0; e < n; ++e) {
+        const float4 ent = seg[e];
+        const int j = __float_as_int(ent.x);
+        const int sidx = S.map[j];
 #pragma unroll
-        for (int t = 0; t < GB; ++t) {
-          const bool live = e0 + t < n;
-          ent[t] = live ? seg[e0 + t] : make_float4(__int_as_float(0), 0.f, 0.f, 0.f);
-          sidx[t] = live ? (int)S.map[__float_as_int(ent[t].x)] : -2;   // -2: padding, -1: unbound column
+        for (int h = 0; h < NH; ++h) {
+          const float pw = h == 0 ? ent.z : ent.w;
 #pragma unroll
-          for (int h = 0; h < NH; ++h)
-#pragma unroll
-            for (int k = 0; k < L4; ++k)
-              if (sidx[t] >= 0) cur[t][h][k] = S.slot_acc[((size_t)sidx[t] * NH + h) * P.lanes4 + tid + k * TALL_THREADS];
-        }
-#pragma unroll
-        for (int t = 0; t < GB; ++t) {
-          const int j = __float_as_int(ent[t].x);
-#pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            const float pw = h == 0 ? ent[t].z : ent[t].w;
-#pragma unroll
-            for (int k = 0; k < L4; ++k) {
-              if (!ok[k]) continue;
-              if (sidx[t] >= 0) {
-                float4 c = cur[t][h][k];
-                c.x = fmaf(pw, g1[k].x, c.x);
-                c.y = fmaf(pw, g1[k].y, c.y);
-                c.z = fmaf(pw, g1[k].z, c.z);
-                c.w = fmaf(pw, g1[k].w, c.w);
-                S.slot_acc[((size_t)sidx[t] * NH + h) * P.lanes4 + tid + k * TALL_THREADS] = c;
-              } else if (sidx[t] == -1) {
-                const float4 add = make_float4(pw * g1[k].x, pw * g1[k].y, pw * g1[k].z, pw * g1[k].w);
-                atomicAdd(reinterpret_cast<float4*>(P.d_y + (y_off[k] + j * row_stride + h * P.C)), add);
-              }
+          for (int k = 0; k < L4; ++k) {
+            if (!ok[k]) continue;
+            const float4 add = make_float4(pw * g1[k].x, pw * g1[k].y, pw * g1[k].z, pw * g1[k].w);
+            if (sidx >= 0) {
+              float4* cell = S.slot_acc + ((size_t)sidx * NH + h) * P.lanes4 + tid + k * TALL_THREADS;
+              float4 cur = *cell;
+              cur.x += add.x;
+              cur.y += add.y;
+              cur.z += add.z;
+              cur.w += add.w;
+              *cell = cur;
+            } else {
+              atomicAdd(reinterpret_cast<float4*>(P.d_y + (y_off[k] + j * row_stride + h * P.C)), add);
             }
           }
         }
