@@ -5,6 +5,10 @@
 ``dist2att`` + ``convolution`` pair (pit.py:46-57, 133-144, 190-200, 247-258) and, for the
 self stage, the ``torch.cat`` of pit.py:44.  Nothing of size N x M is materialised.
 
+``torch.compile``: the entry points are marked ``torch.compiler.disable`` -- the scripts' ``torch.compile(model)``
+(train_darcy.py:112) compiles the surrounding MLPs and runs these ops as opaque eager calls (a graph break each);
+the kernels never depend on a tracing compiler.
+
 Autograd: gradients flow to ``values`` and to the per-head ``scale`` (and from there to
 ``lmda`` through ordinary torch ops); meshes are constants, as at every call site of the
 reference.  No gradient flows through the quantile.
@@ -301,6 +305,7 @@ class _PositionAttention(torch.autograd.Function):
         return d_values, d_scale, None, None, None, None, None, None
 
 
+@torch.compiler.disable
 def position_attention(mesh_out: torch.Tensor, mesh_in: torch.Tensor, values: torch.Tensor, scale: torch.Tensor,
                        locality: float, variant: str = "euclid", self_concat: bool = False) -> torch.Tensor:
     """out[b, n, h*D + d] = sum_j softmax_j(-s_h d2(n, j) | quantile mask)[j] * values[b, j, d].
@@ -368,6 +373,7 @@ class _DecoderTail(torch.autograd.Function):
         return d_y, d_scale.reshape(scale_shape), d_b1, d_w2, d_b2, None, None, None, None
 
 
+@torch.compiler.disable
 def decoder_tail_supported(mesh_in: torch.Tensor, values: torch.Tensor, n_head: int, hidden: int, out_dim: int) -> bool:
     """True when the fused decoder-tail kernels cover this configuration (shared mesh, M <= 1024, H <= 2, ...)."""
     if mesh_in.dim() != 2 or not values.is_cuda or values.dtype != torch.float32:
@@ -376,6 +382,7 @@ def decoder_tail_supported(mesh_in: torch.Tensor, values: torch.Tensor, n_head: 
     return bool(_cabi.lib.pit_decoder_tail_supported(C.byref(prob), out_dim))
 
 
+@torch.compiler.disable
 def decoder_tail(mesh_out, mesh_in, values, scale, locality, w1, b1, w2, b2, variant: str = "euclid") -> torch.Tensor:
     """Fused `de(up(mesh_out, mesh_in, values))`: (B, M, D) latent features -> (B, N, out_dim).
 

@@ -102,3 +102,20 @@ def test_graphed_step_matches_eager(cuda_device):
         assert abs(float(loss_g) - float(loss_e)) <= 1e-4 * abs(float(loss_e))
     for a, b in zip(w.model.parameters(), ref_model.parameters()):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+
+
+def test_torch_compile_wraps_the_model(cuda_device):
+    """The scripts call torch.compile(model) (train_darcy.py:112): the fused ops are opaque to Dynamo and results match eager."""
+    from position_induced_transformer_b200 import workloads
+    gen = torch.Generator().manual_seed(9)
+    w = workloads.make_darcy(43, batch=2).to(cuda_device)
+    (coeff,), target = w.make_batch(gen, 2)
+    coeff, target = coeff.to(cuda_device), target.to(cuda_device)
+    mesh = w.meshes[0]
+    eager = w.model(mesh, coeff, mesh)
+    compiled = torch.compile(w.model)
+    out = compiled(mesh, coeff, mesh)
+    loss = w.loss(target, out)
+    loss.backward()
+    assert rel_linf(out.detach(), eager.detach()) <= 1e-3       # Inductor may reassociate the TF32/fp32 MLP arithmetic
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in w.model.parameters())
