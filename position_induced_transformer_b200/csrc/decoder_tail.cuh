@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(TALL_THREADS, (L4 == 1) ? 4 : 1) tail_bwd_kern
       }
       __syncthreads();
       const bool overflow = S.ctl[1] != 0;
+      __syncthreads();  // every thread has read the flag before thread 0 may reset it
       if (!overflow) break;
       if (attempt == 0) {
         tail_flush_slots<NH, L4>(P, S, y_off, ok, tid);

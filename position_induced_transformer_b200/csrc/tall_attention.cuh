@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(TALL_THREADS) tall_bwd_kernel(const TallParams
         }
         __syncthreads();
         const bool overflow = S.ctl[1] != 0;
+        __syncthreads();  // every thread has read the flag before thread 0 may reset it
         if (!overflow) break;
         if (attempt == 0) {
           tall_flush_slots<L4>(P, S, val_off, ok, tid);
