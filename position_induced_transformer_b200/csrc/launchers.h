@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "decoder_tail.cuh"
+#include "decoder_tail_mma.cuh"
 #include "dense_attention.cuh"
 #include "local_attention.cuh"
 #include "rowstat.cuh"
@@ -40,6 +41,8 @@ cudaError_t tall_backward(int geo, const TallPlan& plan, const TallParams& P, bo
 // tu_tail_fwd.cu / tu_tail_bwd.cu
 cudaError_t tail_forward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
 cudaError_t tail_backward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
+// tu_tail_mma_fwd.cu / tu_tail_mma_bwd.cu  (plan.rows_per_unit counts 16-row tiles per CTA)
+cudaError_t tail_mma_forward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
 // tu_wide.cu
 int wide_pad(int width);
 cudaError_t wide_forward(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);

@@ -378,6 +378,37 @@ TallPlan plan_tail_bwd(const pit_problem_t* p, int out_dim) {
   return c;
 }
 
+// Tensor-core variant (decoder_tail_mma.cuh): hidden width 32, 64 or 128 and B*C a multiple of 128.
+bool tail_mma_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PIT_TAIL_MMA");  // debugging switch: "0" keeps the decoder tail on the SIMT gather kernels
+    cached = (e && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+bool tail_mma_eligible(const pit_problem_t* p, int out_dim) {
+  const int c = p->dim;
+  return tail_mma_enabled() && tail_eligible(p, out_dim) && (c == 32 || c == 64 || c == 128) && ((int64_t)p->batch * c) % pit::TM_CHUNK == 0;
+}
+
+TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
+  TallPlan c{};
+  if (!tail_mma_eligible(p, out_dim)) return c;
+  c.cpl = cpl_of(p->n_in);
+  c.smem = pit::tm_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim);
+  if (c.smem > (size_t)max_smem_optin() - 1024) return c;
+  const int tiles = (p->n_out + pit::TM_ROWS - 1) / pit::TM_ROWS;
+  const int target = sm_count() * 2;
+  int per_cta = (tiles + target - 1) / target;
+  per_cta = (per_cta + pit::TM_ROUND - 1) / pit::TM_ROUND * pit::TM_ROUND;
+  c.rows_per_unit = per_cta;
+  c.grid = (tiles + per_cta - 1) / per_cta;
+  c.ok = true;
+  return c;
+}
+
 pit::TailParams tail_params(const pit_problem_t* p, const TallPlan& c, const float* mesh_out, const float* mesh_in,
                             const float* period, const float* y, const float* scale, const pit_rowstat_t* st,
                             const float* b1, const float* w2, const float* b2, int out_dim) {
@@ -695,13 +726,17 @@ int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, cons
   if (int rc = check_stat(p, stat, period)) return rc;
   if (!tail_eligible(p, out_dim)) return fail(PIT_ERR_ARG, "decoder tail: unsupported configuration (see pit_decoder_tail_supported)");
   if (!aligned16(y) || !aligned16(b1) || !aligned16(w2)) return fail(PIT_ERR_ARG, "decoder tail: y, b1, w2 must be 16-byte aligned");
-  const TallPlan plan = plan_tail_fwd(p);
+  const TallPlan mma = plan_tail_mma_fwd(p, out_dim);
+  const TallPlan plan = mma.ok ? mma : plan_tail_fwd(p);
   if (!plan.ok) return fail(PIT_ERR_ARG, "decoder tail: no launch plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
   P.out = out;
   P.rowsum = rowsum;
-  PIT_CUDA(launch::tail_forward(geo_of(p), plan, P, st));
+  if (mma.ok)
+    PIT_CUDA(launch::tail_mma_forward(geo_of(p), plan, P, st));
+  else
+    PIT_CUDA(launch::tail_forward(geo_of(p), plan, P, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }
