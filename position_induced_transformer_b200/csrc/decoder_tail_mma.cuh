@@ -7,22 +7,26 @@
 //
 //     pre^T [(b,c) x 16 rows] = Y^T [(b,c) x candidates] . P^T [candidates x 16 rows]        (per head, summed)
 //
-// is a small dense product at ~50 % density -- worth moving to the tensor pipe, which has ~8x the FMA rate of the
-// fp32 pipe even after the 3xTF32 split.  The mask itself is still decided exactly as in the SIMT kernels (bit-exact
-// d2, per-head cut, fp32 weights); only the products are split:  hi*hi + lo*hi + hi*lo with fp32 accumulation
-// (error ~2^-21, inside the 1e-5 parity budget).
+// is a small dense product at ~50 % density -- worth moving to the tensor pipe, which has several times the FMA rate
+// of the fp32 pipe even after the 3xTF32 split.  The mask itself is still decided exactly as in the SIMT kernels
+// (bit-exact d2, per-head cut, fp32 weights); only the products are split:  hi*hi + lo*hi + hi*lo with fp32
+// accumulation (error ~2^-21, inside the 1e-5 parity budget).
 //
-// Work split.  A CTA (4 warps) walks its tiles in rounds of 4:
-//   phase 1  warp w "prepares" tile w of the round: scans the M columns held in registers against the 16 rows
+// Work split.  A CTA (4 or 8 warps) walks its tiles in rounds of 4:
+//   phase 1  warp w < 4 "prepares" tile w of the round: scans the M columns held in registers against the 16 rows
 //            (head-independent d2-space pre-filter), ballot-compacts the candidate list, evaluates the unnormalised
 //            weights P[h][row][cand] (and d2) into a shared-memory block, and the row sums;
-//   phase 2  for every prepared tile, warp w owns the 128-column chunk(s) w, w+4, ... of the B*C-wide hidden vector:
-//            operand A = Y^T straight from global/L1 (each thread reads 16 contiguous floats of two candidate rows:
-//            the column order inside an m16 tile is permuted so that fragments are 128-bit loads), operand B = P^T
-//            from the shared block (conflict-free with the 36-float pitch), accumulators [128 cols x 16 rows] in
-//            64 registers; epilogue = bias + exact GELU + C->O projection on the fragments.
+//   phase 2  for every prepared tile, warp w owns the 64-column chunk(s) w, w+nwarps, ... of the B*C-wide hidden
+//            vector: operand A = Y^T straight from global/L1 (a thread reads 8 contiguous floats of two candidate
+//            rows; the column order inside an m16 tile is permuted so that a fragment is two 64-bit loads),
+//            operand B = P^T from the shared block (conflict-free with the 36-float pitch), accumulators
+//            [64 cols x 16 rows] in 32 registers; epilogue = bias + exact GELU + C->O projection on the fragments.
 // The transposed orientation (columns on the MMA m axis, rows on n) is what makes the backward cheap: the
-// accumulator fragment of g1^T is, register for register, the A fragment of dY^T = g1^T . P (reduction over rows).
+// accumulator fragment of g1^T is, register for register, the A fragment of dY^T = g1^T . P (reduction over rows),
+// and the scale gradient follows from the same fragments with P (d2 - m) as the second B operand:
+//     ds_h = -sum_{j,col} Y_h[j,col] (sum_i P^_ij (d2_ij - m_i) g1[i,col]).
+// dY is accumulated without atomics in shared-memory slots bound to latent columns (one owner thread per cell), as
+// in tall_bwd_kernel, and flushed with vector REDs.
 //
 // Tiles whose candidate list exceeds one 32-column block (incoherent meshes, unmasked decoders) are handled by
 // recomputing further blocks on the fly -- slower, same results.
@@ -31,11 +35,14 @@
 
 namespace pit {
 
-constexpr int TM_ROWS = 16;    // rows per tile (two n8 MMA tiles)
-constexpr int TM_KT = 32;      // candidates per weight block
-constexpr int TM_LD = 36;      // pitch of a block row in floats: fragment reads hit 32 distinct banks
-constexpr int TM_CHUNK = 128;  // hidden-vector columns per warp pass (eight m16 MMA tiles)
-constexpr int TM_ROUND = TALL_WARPS;  // tiles prepared per round (one per warp)
+constexpr int TM_ROWS = 16;   // rows per tile (two n8 MMA tiles)
+constexpr int TM_KT = 32;     // candidates per weight block
+constexpr int TM_LD = 36;     // pitch of a block row in floats: fragment reads hit 32 distinct banks
+constexpr int TM_MT = 4;      // m16 MMA tiles per warp pass
+constexpr int TM_CHUNK = 16 * TM_MT;  // hidden-vector columns per warp pass
+constexpr int TM_TPC = 2 * TM_MT;     // contiguous columns a thread owns inside a chunk
+constexpr int TM_ROUND = 4;   // tiles prepared per round (one per warp 0..3)
+constexpr int TM_MAX_WARPS = 8;
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -47,6 +54,30 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
 // (truncated) high part and only the residual needs arithmetic; weights use a rounded high part (half the residual).
 __device__ __forceinline__ uint32_t tm_trunc_lo(float x) { return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u)); }
 __device__ __forceinline__ float tm_round_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+// Exact-GELU pair as gelu_pair (A&S 7.1.26, |err| <= 1.5e-7) with flush-to-zero approximations, which drop the
+// denormal-range fix-up code around MUFU.EX2 / MUFU.RCP: 14 instructions instead of ~21.
+__device__ __forceinline__ void tm_gelu_pair(float x, float& g, float& dg) {
+  const float ax = fabsf(x);
+  const float u = ax * 0.84932180028801904f;  // sqrt(log2(e) / 2): exp(-x^2/2) = 2^(-u^2)
+  float e, t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752f, 1.f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, e, 1.f);
+  const float phi = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+  g = x * phi;
+  dg = fmaf(x * 0.3989422804014327f, e, phi);
+}
+__device__ __forceinline__ float tm_gelu(float x) {
+  float g, dg;
+  tm_gelu_pair(x, g, dg);
+  return g;
+}
 
 // Per-row constants of a tile row, held by lanes i and i+16 of the preparing warp.
 template <int GEO, int NH>
@@ -133,19 +164,19 @@ __device__ __forceinline__ void tm_block(const TailParams& P, const TmRow<GEO, N
 // Shared-memory image of a prepared tile.
 template <int NH, bool BWD>
 struct TmTile {
-  float p[NH][TM_ROWS][TM_LD];              // unnormalised weights of block 0 (or of the block being processed)
-  float d2[BWD ? TM_ROWS : 1][TM_LD];       // squared distances (backward only)
-  float inv_l[NH][TM_ROWS];                 // 1 / row sum (0 for rows past the end)
-  float m[NH][TM_ROWS];                     // backward: sum_j P^ d2
+  float p[NH][TM_ROWS][TM_LD];         // unnormalised weights of block 0 (or of the block being processed)
+  float d2[BWD ? TM_ROWS : 1][TM_LD];  // squared distances (backward only)
+  float inv_l[NH][TM_ROWS];            // 1 / row sum (0 for rows past the end)
+  float m[NH][TM_ROWS];                // backward: sum_j P^ d2
   int cnt;
   int pad[3];
 };
 
-// pre^T += Y_h^T . P_h^T for one block of one tile and one 128-column chunk.
-//   acc[mt][nt][.]: column 16*g + mt (+8 for registers 2,3) of the chunk, rows 8*nt + 2*t (+1 for registers 1,3).
-// y_chunk points at Y[b, 0, 0, c] for this thread's 16 columns; row j of head h sits NH*C*j + h*C floats further.
+// pre^T += Y_h^T . P_h^T for one block of one tile and one 64-column chunk.
+//   acc[mt][nt][e]: chunk column TPC*g + 2*mt + (e >> 1), tile row 8*nt + 2*t + (e & 1).
+// y_chunk points at Y[b, 0, 0, c] for this thread's TPC columns; row j of head h sits (NH*j + h)*C floats further.
 template <int NH>
-__device__ __forceinline__ void tm_mma_block(float (&acc)[8][2][4], const float (*p)[TM_ROWS][TM_LD], const float (*inv_l)[TM_ROWS],
+__device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const float (*p)[TM_ROWS][TM_LD], const float (*inv_l)[TM_ROWS],
                                              const int16_t* cand, int cnt, int kb, const float* y_chunk, int C, int g, int t) {
   const int base = kb * TM_KT;
   const int ksteps = (min(cnt - base, TM_KT) + 7) >> 3;
@@ -155,14 +186,13 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[8][2][4], const float 
     for (int ks = 0; ks < ksteps; ++ks) {
       const int ka = base + ks * 8 + t, kc = ka + 4;
       const int ja = ka < cnt ? (int)cand[ka] : 0, jb = kc < cnt ? (int)cand[kc] : 0;
-      const float4* ra = reinterpret_cast<const float4*>(y_chunk + ((size_t)ja * NH + h) * C);
-      const float4* rb = reinterpret_cast<const float4*>(y_chunk + ((size_t)jb * NH + h) * C);
-      float ya[16], yb[16];
+      const float2* ra = reinterpret_cast<const float2*>(y_chunk + ((size_t)ja * NH + h) * C);
+      const float2* rb = reinterpret_cast<const float2*>(y_chunk + ((size_t)jb * NH + h) * C);
+      float2 ya[TM_MT], yb[TM_MT];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const float4 a = __ldg(ra + v), b = __ldg(rb + v);
-        ya[4 * v] = a.x, ya[4 * v + 1] = a.y, ya[4 * v + 2] = a.z, ya[4 * v + 3] = a.w;
-        yb[4 * v] = b.x, yb[4 * v + 1] = b.y, yb[4 * v + 2] = b.z, yb[4 * v + 3] = b.w;
+      for (int mt = 0; mt < TM_MT; ++mt) {
+        ya[mt] = __ldg(ra + mt);
+        yb[mt] = __ldg(rb + mt);
       }
       uint32_t bh[2][2], bl[2][2];
 #pragma unroll
@@ -174,9 +204,9 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[8][2][4], const float 
         bl[nt][0] = __float_as_uint(p0 - h0), bl[nt][1] = __float_as_uint(p1 - h1);
       }
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) {
-        const uint32_t ah[4] = {__float_as_uint(ya[mt]), __float_as_uint(ya[8 + mt]), __float_as_uint(yb[mt]), __float_as_uint(yb[8 + mt])};
-        const uint32_t al[4] = {tm_trunc_lo(ya[mt]), tm_trunc_lo(ya[8 + mt]), tm_trunc_lo(yb[mt]), tm_trunc_lo(yb[8 + mt])};
+      for (int mt = 0; mt < TM_MT; ++mt) {
+        const uint32_t ah[4] = {__float_as_uint(ya[mt].x), __float_as_uint(ya[mt].y), __float_as_uint(yb[mt].x), __float_as_uint(yb[mt].y)};
+        const uint32_t al[4] = {tm_trunc_lo(ya[mt].x), tm_trunc_lo(ya[mt].y), tm_trunc_lo(yb[mt].x), tm_trunc_lo(yb[mt].y)};
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           mma_tf32_16x8x8(acc[mt][nt], al, bh[nt]);
@@ -190,19 +220,19 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[8][2][4], const float 
 
 __host__ __device__ inline size_t tm_align(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t tm_cand_bytes(int M) { return tm_align((size_t)M * 2); }
-template <int NH, bool BWD>
-__host__ __device__ inline size_t tm_tiles_bytes(int M) {
-  return 2 * TM_ROUND * (tm_align(sizeof(TmTile<NH, BWD>)) + tm_cand_bytes(M));
+__host__ __device__ inline size_t tm_tile_bytes(int nh, bool bwd) {
+  return nh == 1 ? (bwd ? tm_align(sizeof(TmTile<1, true>)) : tm_align(sizeof(TmTile<1, false>)))
+                 : (bwd ? tm_align(sizeof(TmTile<2, true>)) : tm_align(sizeof(TmTile<2, false>)));
 }
 __host__ __device__ inline size_t tm_fwd_smem_bytes(int nh, int M, int C, int O) {
-  return (nh == 1 ? tm_tiles_bytes<1, false>(M) : tm_tiles_bytes<2, false>(M)) + tm_align((size_t)C * (1 + O) * 4);
+  return 2 * TM_ROUND * (tm_tile_bytes(nh, false) + tm_cand_bytes(M)) + tm_align((size_t)C * (1 + O) * 4);
 }
 
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
 template <int GEO, int CPL, int NH>
-__global__ void __launch_bounds__(TALL_THREADS, 2) tail_mma_fwd_kernel(const TailParams P) {
+__global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(const TailParams P) {
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TmTile<NH, false>;
   const size_t tile_stride = tm_align(sizeof(Tile));
@@ -210,19 +240,13 @@ __global__ void __launch_bounds__(TALL_THREADS, 2) tail_mma_fwd_kernel(const Tai
   const size_t cand_stride = tm_cand_bytes(P.M);
   float* par = reinterpret_cast<float*>(cand_base + 2 * TM_ROUND * cand_stride);  // [b1 (C) | W2 (O x C)]
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const float period = P.period ? __ldg(P.period) : 0.f;
-  Point<GEO> col[CPL];
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    const int j = c * 32 + lane;
-    col[c] = load_point<GEO>(P.mesh_in, j < P.M ? j : 0, P.sd);
-  }
   float s[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
-  for (int i = tid; i < P.C * (1 + P.O); i += TALL_THREADS) par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
+  for (int i = tid; i < P.C * (1 + P.O); i += blockDim.x) par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
   float b2r[TAIL_MAX_OUT];
 #pragma unroll
   for (int o = 0; o < TAIL_MAX_OUT; ++o) b2r[o] = o < P.O ? __ldg(P.b2 + o) : 0.f;
@@ -231,14 +255,20 @@ __global__ void __launch_bounds__(TALL_THREADS, 2) tail_mma_fwd_kernel(const Tai
   const int n_tiles = (P.N + TM_ROWS - 1) / TM_ROWS;
   const int tile_begin = blockIdx.x * P.rows_per_unit;  // rows_per_unit counts tiles here
   const int tile_end = min(n_tiles, tile_begin + P.rows_per_unit);
-  const int c0 = (16 * g) % P.C;          // this thread's 16 hidden channels (the same in every chunk: C divides 128)
-  const int group = P.C / 16;             // lanes-of-g sharing a sample
+  const int c0 = (TM_TPC * g) % P.C;  // this thread's hidden channels (the same in every chunk: C divides the chunk width)
+  const int group = P.C / TM_TPC;     // consecutive g sharing a sample
   int round = 0;
   for (int tb = tile_begin; tb < tile_end; tb += TM_ROUND, ++round) {
     const int in_round = min(TM_ROUND, tile_end - tb);
     const int set = (round & 1) * TM_ROUND;
-    // ---- phase 1: one tile per warp ----
+    // ---- phase 1: one tile per warp (warps 0..3) ----
     if (warp < in_round) {
+      Point<GEO> col[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int j = c * 32 + lane;
+        col[c] = load_point<GEO>(P.mesh_in, j < P.M ? j : 0, P.sd);
+      }
       Tile* T = reinterpret_cast<Tile*>(tall_smem_raw + (set + warp) * tile_stride);
       int16_t* cand = reinterpret_cast<int16_t*>(cand_base + (set + warp) * cand_stride);
       const int row = (tb + warp) * TM_ROWS + (lane & 15);
@@ -268,15 +298,14 @@ __global__ void __launch_bounds__(TALL_THREADS, 2) tail_mma_fwd_kernel(const Tai
       const int cnt = T->cnt;
       const int nkb = (cnt + TM_KT - 1) / TM_KT;
       const int row0 = (tb + v) * TM_ROWS;
-      for (int ch0 = 0; ch0 < chunks; ch0 += TALL_WARPS) {
+      for (int ch0 = 0; ch0 < chunks; ch0 += nwarps) {
         const int chunk = ch0 + warp;
         const bool active = chunk < chunks;
-        const int colbase = chunk * TM_CHUNK + 16 * g;
-        const int b = active ? colbase / P.C : 0;
+        const int b = active ? (chunk * TM_CHUNK + TM_TPC * g) / P.C : 0;
         const float* y_chunk = P.y + (size_t)b * P.M * NH * P.C + c0;
-        float acc[8][2][4];
+        float acc[TM_MT][2][4];
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt)
+        for (int mt = 0; mt < TM_MT; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -296,24 +325,24 @@ __global__ void __launch_bounds__(TALL_THREADS, 2) tail_mma_fwd_kernel(const Tai
           if (active) tm_mma_block<NH>(acc, T->p, T->inv_l, cand, cnt, kb, y_chunk, P.C, g, t);
         }
         if (!active) continue;
-        // epilogue: out[b, row, o] = b2[o] + sum_c W2[o, c] gelu(b1[c] + pre[c]); the thread holds channels c0..c0+15 of rows
-        // 2t, 2t+1, 2t+8, 2t+9; the lanes of `group` consecutive g share the sample.
+        // epilogue: out[b, row, o] = b2[o] + sum_c W2[o, c] gelu(b1[c] + pre[c]); the thread holds channels c0..c0+TPC-1 of
+        // rows 2t, 2t+1, 2t+8, 2t+9; the lanes of `group` consecutive g share the sample.
         float part[TAIL_MAX_OUT][4];
 #pragma unroll
         for (int o = 0; o < TAIL_MAX_OUT; ++o)
 #pragma unroll
           for (int q = 0; q < 4; ++q) part[o][q] = 0.f;
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
+        for (int mt = 0; mt < TM_MT; ++mt) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            const int c = c0 + mt + 8 * half;
+            const int c = c0 + 2 * mt + half;
             const float bias = par[c];
             float hid[4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-              for (int e = 0; e < 2; ++e) hid[nt * 2 + e] = gelu_erf(acc[mt][nt][half * 2 + e] + bias);
+              for (int e = 0; e < 2; ++e) hid[nt * 2 + e] = tm_gelu(acc[mt][nt][half * 2 + e] + bias);
 #pragma unroll
             for (int o = 0; o < TAIL_MAX_OUT; ++o) {
               if (o < P.O) {
@@ -338,6 +367,409 @@ __global__ void __launch_bounds__(TALL_THREADS, 2) tail_mma_fwd_kernel(const Tai
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------
+struct TmBwdSmem {
+  unsigned char* tiles;  // [TM_ROUND] TmTile<NH, true>
+  unsigned char* cand;   // [TM_ROUND][M] int16
+  float* slot_acc;       // [n_slots][NH][W], columns rotated inside 32-float windows by 4*(slot & 7)
+  float* priv;           // [(1+O)*TPC][threads]: per-thread partial sums of d_b1 and d_w2 for its channels
+  float* par;            // [C + O*C]: b1 then W2
+  float* gpar;           // [C + O*C]: CTA-level reduction of d_b1, d_w2
+  float* red;            // [TM_MAX_WARPS]
+  int16_t* map;          // [M] column -> slot (-1: unbound)
+  int16_t* slot_j;       // [n_slots]
+  uint8_t* touched;      // [M]
+  int* ctl;
+};
+
+__host__ __device__ inline size_t tm_bwd_smem_bytes(int nh, int M, int W, int C, int O, int n_slots, int threads) {
+  return TM_ROUND * (tm_tile_bytes(nh, true) + tm_cand_bytes(M)) + tm_align((size_t)n_slots * nh * W * 4) +
+         tm_align((size_t)(1 + O) * TM_TPC * threads * 4) + 2 * tm_align((size_t)C * (1 + O) * 4) + 64 + tm_align((size_t)M * 2) +
+         tm_align((size_t)n_slots * 2) + tm_align(M) + 16;
+}
+
+__device__ inline TmBwdSmem tm_bwd_carve(unsigned char* p, int nh, int M, int W, int C, int O, int n_slots, int threads) {
+  TmBwdSmem s{};
+  s.tiles = p;
+  p += TM_ROUND * tm_tile_bytes(nh, true);
+  s.cand = p;
+  p += TM_ROUND * tm_cand_bytes(M);
+  s.slot_acc = reinterpret_cast<float*>(p);
+  p += tm_align((size_t)n_slots * nh * W * 4);
+  s.priv = reinterpret_cast<float*>(p);
+  p += tm_align((size_t)(1 + O) * TM_TPC * threads * 4);
+  s.par = reinterpret_cast<float*>(p);
+  p += tm_align((size_t)C * (1 + O) * 4);
+  s.gpar = reinterpret_cast<float*>(p);
+  p += tm_align((size_t)C * (1 + O) * 4);
+  s.red = reinterpret_cast<float*>(p);
+  p += 64;
+  s.map = reinterpret_cast<int16_t*>(p);
+  p += tm_align((size_t)M * 2);
+  s.slot_j = reinterpret_cast<int16_t*>(p);
+  p += tm_align((size_t)n_slots * 2);
+  s.touched = reinterpret_cast<uint8_t*>(p);
+  p += tm_align(M);
+  s.ctl = reinterpret_cast<int*>(p);
+  return s;
+}
+
+// Position of column x inside the slot row of slot `sidx`: 16-byte groups rotate inside their 128-byte window so that
+// the four lanes of a quad, which address four different slots at the same column, fall into different banks.
+__device__ __forceinline__ int tm_slot_pos(int x, int sidx) { return (x & ~31) | ((x + 4 * (sidx & 7)) & 31); }
+
+// Flush every bound slot into d_y with vector REDs and clear it.  Cells are split over the CTA's threads.
+template <int NH>
+__device__ __forceinline__ void tm_flush_slots(const TailParams& P, const TmBwdSmem& S, int W) {
+  const int used = min(S.ctl[0], P.n_slots);
+  const int w4 = W / 4;
+  for (int i = threadIdx.x; i < used * NH * w4; i += blockDim.x) {
+    const int sidx = i / (NH * w4);
+    const int rem = i - sidx * (NH * w4);
+    const int h = rem / w4, x = (rem - h * w4) * 4;
+    float4* cell = reinterpret_cast<float4*>(S.slot_acc + ((size_t)sidx * NH + h) * W + tm_slot_pos(x, sidx));
+    const int b = x / P.C, c = x - b * P.C;
+    const int j = S.slot_j[sidx];
+    atomicAdd(reinterpret_cast<float4*>(P.d_y + (((size_t)b * P.M + j) * NH + h) * P.C + c), *cell);
+    *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int GEO, int CPL, int NH>
+__global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(const TailParams P) {
+  extern __shared__ __align__(16) unsigned char tall_smem_raw[];
+  using Tile = TmTile<NH, true>;
+  const int W = P.B * P.C;
+  const TmBwdSmem S = tm_bwd_carve(tall_smem_raw, NH, P.M, W, P.C, P.O, P.n_slots, blockDim.x);
+  const size_t tile_stride = tm_align(sizeof(Tile));
+  const size_t cand_stride = tm_cand_bytes(P.M);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const float period = P.period ? __ldg(P.period) : 0.f;
+  float s[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
+  const int n_par = P.C * (1 + P.O);
+  for (int i = tid; i < n_par; i += blockDim.x) {
+    S.par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
+    S.gpar[i] = 0.f;
+  }
+  for (int j = tid; j < P.M; j += blockDim.x) {
+    S.map[j] = -1;
+    S.touched[j] = 0;
+  }
+  for (int i = tid; i < P.n_slots * NH * W; i += blockDim.x) S.slot_acc[i] = 0.f;
+  for (int i = 0; i < (1 + P.O) * TM_TPC; ++i) S.priv[i * blockDim.x + tid] = 0.f;
+  if (tid == 0) {
+    S.ctl[0] = 0;
+    S.ctl[1] = 0;
+  }
+  __syncthreads();
+
+  float ds_head[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) ds_head[h] = 0.f;
+  float db2[TAIL_MAX_OUT];
+#pragma unroll
+  for (int o = 0; o < TAIL_MAX_OUT; ++o) db2[o] = 0.f;
+
+  const int chunks = W / TM_CHUNK;
+  const int n_tiles = (P.N + TM_ROWS - 1) / TM_ROWS;
+  const int tile_begin = blockIdx.x * P.rows_per_unit;
+  const int tile_end = min(n_tiles, tile_begin + P.rows_per_unit);
+  const int c0 = (TM_TPC * g) % P.C;
+  const int group = P.C / TM_TPC;
+  for (int tb = tile_begin; tb < tile_end; tb += TM_ROUND) {
+    const int in_round = min(TM_ROUND, tile_end - tb);
+    // ---- phase 1: one tile per warp (warps 0..3): candidates, weights, d2, 1/l, m ----
+    if (warp < in_round) {
+      Point<GEO> col[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int j = c * 32 + lane;
+        col[c] = load_point<GEO>(P.mesh_in, j < P.M ? j : 0, P.sd);
+      }
+      Tile* T = reinterpret_cast<Tile*>(S.tiles + warp * tile_stride);
+      int16_t* cand = reinterpret_cast<int16_t*>(S.cand + warp * cand_stride);
+      const int row = (tb + warp) * TM_ROWS + (lane & 15);
+      const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row, s);
+      const int cnt = tm_candidates<GEO, CPL, NH>(R, col, P.M, lane, period, cand);
+      float psum[NH], pdsum[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) psum[h] = pdsum[h] = 0.f;
+      const int nkb = (cnt + TM_KT - 1) / TM_KT;
+      for (int kb = nkb - 1; kb >= 0; --kb)
+        tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], &T->d2[0][0], psum, pdsum);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float pd = pdsum[h] + __shfl_xor_sync(FULL, pdsum[h], 16);
+        if (lane < TM_ROWS) {
+          const float inv = R.valid ? 1.f / __ldg(P.rowsum + (int64_t)h * P.N + row) : 0.f;
+          T->inv_l[h][lane] = inv;
+          T->m[h][lane] = pd * inv;
+        }
+      }
+      for (int k = lane; k < cnt; k += 32) S.touched[cand[k]] = 1;
+      if (lane == 0) T->cnt = cnt;
+    }
+    __syncthreads();
+    // bind a slot to every column touched in this round; flush everything once if the set is full
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      for (int j = tid; j < P.M; j += blockDim.x) {
+        if (S.touched[j] && S.map[j] < 0) {
+          const int sidx = atomicAdd(&S.ctl[0], 1);
+          if (sidx < P.n_slots) {
+            S.map[j] = (int16_t)sidx;
+            S.slot_j[sidx] = (int16_t)j;
+          } else {
+            S.ctl[1] = 1;
+          }
+        }
+      }
+      __syncthreads();
+      const bool overflow = S.ctl[1] != 0;
+      __syncthreads();  // every thread has read the flag before thread 0 may reset it
+      if (!overflow) break;
+      if (attempt == 0) {
+        tm_flush_slots<NH>(P, S, W);
+        __syncthreads();
+        for (int j = tid; j < P.M; j += blockDim.x) S.map[j] = -1;
+        if (tid == 0) {
+          S.ctl[0] = 0;
+          S.ctl[1] = 0;
+        }
+        __syncthreads();
+      } else {
+        if (tid == 0) {
+          S.ctl[0] = P.n_slots;
+          S.ctl[1] = 0;
+        }
+      }
+    }
+    for (int j = tid; j < P.M; j += blockDim.x) S.touched[j] = 0;
+    __syncthreads();
+    // ---- phase 2 ----
+    for (int v = 0; v < in_round; ++v) {
+      Tile* T = reinterpret_cast<Tile*>(S.tiles + v * tile_stride);
+      const int16_t* cand = reinterpret_cast<const int16_t*>(S.cand + v * cand_stride);
+      const int cnt = T->cnt;
+      const int nkb = (cnt + TM_KT - 1) / TM_KT;
+      const int row0 = (tb + v) * TM_ROWS;
+      for (int ch0 = 0; ch0 < chunks; ch0 += nwarps) {
+        const int chunk = ch0 + warp;
+        const bool active = chunk < chunks;
+        const int xcol = chunk * TM_CHUNK + TM_TPC * g;  // first of this thread's columns of the B*C-wide vector
+        const int b = active ? xcol / P.C : 0;
+        const float* y_chunk = P.y + (size_t)b * P.M * NH * P.C + c0;
+        float acc[TM_MT][2][4];
+#pragma unroll
+        for (int mt = 0; mt < TM_MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+        // (a) hidden pre-activation, as in the forward
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (nkb > 1) {
+            __syncthreads();
+            if (warp == 0) {
+              const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row0 + (lane & 15), s);
+              float ps[NH], pd[NH];
+#pragma unroll
+              for (int h = 0; h < NH; ++h) ps[h] = pd[h] = 0.f;
+              tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], &T->d2[0][0], ps, pd);
+            }
+            __syncthreads();
+          }
+          if (active) tm_mma_block<NH>(acc, T->p, T->inv_l, cand, cnt, kb, y_chunk, P.C, g, t);
+        }
+        // (b) g1 = gelu'(pre) * (W2^T dOut[b, row, :]) in place; parameter-gradient partials
+        if (active) {
+          float go[4][TAIL_MAX_OUT];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int row = row0 + (q >> 1) * 8 + 2 * t + (q & 1);
+#pragma unroll
+            for (int o = 0; o < TAIL_MAX_OUT; ++o) {
+              go[q][o] = (o < P.O && row < P.N) ? __ldg(P.d_out + ((int64_t)b * P.N + row) * P.O + o) : 0.f;
+              if ((g % group) == 0) db2[o] += go[q][o];
+            }
+          }
+#pragma unroll
+          for (int mt = 0; mt < TM_MT; ++mt) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int i = 2 * mt + half;
+              const int c = c0 + i;
+              const float bias = S.par[c];
+              float wv[TAIL_MAX_OUT], dw[TAIL_MAX_OUT];
+#pragma unroll
+              for (int o = 0; o < TAIL_MAX_OUT; ++o) {
+                wv[o] = o < P.O ? S.par[(1 + o) * P.C + c] : 0.f;
+                dw[o] = 0.f;
+              }
+              float gsum = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float hid, dhid;
+                tm_gelu_pair(acc[mt][q >> 1][half * 2 + (q & 1)] + bias, hid, dhid);
+                float up = 0.f;
+#pragma unroll
+                for (int o = 0; o < TAIL_MAX_OUT; ++o) {
+                  if (o < P.O) {
+                    up = fmaf(go[q][o], wv[o], up);
+                    dw[o] = fmaf(go[q][o], hid, dw[o]);
+                  }
+                }
+                const float g1 = up * dhid;
+                acc[mt][q >> 1][half * 2 + (q & 1)] = g1;
+                gsum += g1;
+              }
+              S.priv[i * blockDim.x + tid] += gsum;
+#pragma unroll
+              for (int o = 0; o < TAIL_MAX_OUT; ++o)
+                if (o < P.O) S.priv[((1 + o) * TM_TPC + i) * blockDim.x + tid] += dw[o];
+            }
+          }
+        }
+        // (c) dY^T += g1^T . P^  and  dZ^T = g1^T . (P^ (d2 - m)) per head and group of 8 candidates
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (nkb > 1) {
+            __syncthreads();
+            if (warp == 0) {
+              const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row0 + (lane & 15), s);
+              float ps[NH], pd[NH];
+#pragma unroll
+              for (int h = 0; h < NH; ++h) ps[h] = pd[h] = 0.f;
+              tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], &T->d2[0][0], ps, pd);
+            }
+            __syncthreads();
+          }
+          if (!active) continue;
+          const int base = kb * TM_KT;
+          const int groups8 = (min(cnt - base, TM_KT) + 7) >> 3;
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            for (int ct = 0; ct < groups8; ++ct) {
+              float dy[TM_MT][4], dz[TM_MT][4];
+#pragma unroll
+              for (int mt = 0; mt < TM_MT; ++mt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dy[mt][e] = dz[mt][e] = 0.f;
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                // B fragments: k-slot t <-> tile row 8nt+2t, k-slot t+4 <-> row 8nt+2t+1; n = candidate 8ct+g
+                uint32_t ph[2], pl[2], zh[2], zl[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int r = 8 * nt + 2 * t + e;
+                  const float pn = T->p[h][r][ct * 8 + g] * T->inv_l[h][r];
+                  const float pz = pn * (T->d2[r][ct * 8 + g] - T->m[h][r]);
+                  const float h0 = tm_round_hi(pn), h1 = tm_round_hi(pz);
+                  ph[e] = __float_as_uint(h0), pl[e] = __float_as_uint(pn - h0);
+                  zh[e] = __float_as_uint(h1), zl[e] = __float_as_uint(pz - h1);
+                }
+#pragma unroll
+                for (int mt = 0; mt < TM_MT; ++mt) {
+                  // A fragments: the accumulator registers of g1^T, reordered (m = column, k = row)
+                  const float a0 = acc[mt][nt][0], a1 = acc[mt][nt][2], a2 = acc[mt][nt][1], a3 = acc[mt][nt][3];
+                  const uint32_t ah[4] = {__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3)};
+                  const uint32_t al[4] = {tm_trunc_lo(a0), tm_trunc_lo(a1), tm_trunc_lo(a2), tm_trunc_lo(a3)};
+                  mma_tf32_16x8x8(dy[mt], al, ph);
+                  mma_tf32_16x8x8(dy[mt], ah, pl);
+                  mma_tf32_16x8x8(dy[mt], ah, ph);
+                  mma_tf32_16x8x8(dz[mt], al, zh);
+                  mma_tf32_16x8x8(dz[mt], ah, zl);
+                  mma_tf32_16x8x8(dz[mt], ah, zh);
+                }
+              }
+              // dy/dz[mt][e]: column TPC*g + 2*mt + (e >> 1), candidate 8ct + 2t + (e & 1)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int ci = base + ct * 8 + 2 * t + e;
+                if (ci < cnt) {
+                  const int j = cand[ci];
+                  // scale gradient: -sum Y_h[j, col] dZ[col, j]
+                  const float2* yr = reinterpret_cast<const float2*>(y_chunk + ((size_t)j * NH + h) * P.C);
+                  float dot = 0.f;
+#pragma unroll
+                  for (int mt = 0; mt < TM_MT; ++mt) {
+                    const float2 yv = __ldg(yr + mt);
+                    dot = fmaf(yv.x, dz[mt][e], dot);
+                    dot = fmaf(yv.y, dz[mt][2 + e], dot);
+                  }
+                  ds_head[h] += dot;
+                  // value gradient: the thread owns these TPC cells of the slot (or of d_y itself if the column is unbound)
+                  const int sidx = S.map[j];
+                  if (sidx >= 0) {
+#pragma unroll
+                    for (int v4 = 0; v4 < TM_TPC / 4; ++v4) {
+                      // positions stay 16-byte groups: the rotation is a multiple of 4 floats; the second group may wrap
+                      float4* c4 = reinterpret_cast<float4*>(S.slot_acc + ((size_t)sidx * NH + h) * W + tm_slot_pos(xcol + 4 * v4, sidx));
+                      float4 cur = *c4;
+                      cur.x += dy[2 * v4][e];
+                      cur.y += dy[2 * v4][2 + e];
+                      cur.z += dy[2 * v4 + 1][e];
+                      cur.w += dy[2 * v4 + 1][2 + e];
+                      *c4 = cur;
+                    }
+                  } else {
+                    float* dst = P.d_y + (((size_t)b * P.M + j) * NH + h) * P.C + c0;
+#pragma unroll
+                    for (int v4 = 0; v4 < TM_TPC / 4; ++v4)
+                      atomicAdd(reinterpret_cast<float4*>(dst + 4 * v4),
+                                make_float4(dy[2 * v4][e], dy[2 * v4][2 + e], dy[2 * v4 + 1][e], dy[2 * v4 + 1][2 + e]));
+                  }
+                }
+              }
+              __syncwarp();  // the lanes of a quad may reach the same slot cell in the next group of candidates
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  tm_flush_slots<NH>(P, S, W);
+
+  // ---- parameter gradients: one reduction per CTA ----
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const float v = warp_sum(ds_head[h]);
+    __syncthreads();
+    if (lane == 0) S.red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      float acc = 0.f;
+      for (int w = 0; w < nwarps; ++w) acc += S.red[w];
+      atomicAdd(P.d_scale + h, -acc);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < TAIL_MAX_OUT; ++o) {
+    if (o >= P.O) continue;  // uniform
+    const float v = warp_sum(db2[o]);
+    __syncthreads();
+    if (lane == 0) S.red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      float acc = 0.f;
+      for (int w = 0; w < nwarps; ++w) acc += S.red[w];
+      atomicAdd(P.d_b2 + o, acc);
+    }
+  }
+  // b1 and W2: per-thread partials (channel c0 + i) -> CTA sums in shared memory -> one RED per address
+  for (int i = 0; i < TM_TPC; ++i) {
+    atomicAdd(&S.gpar[c0 + i], S.priv[i * blockDim.x + tid]);
+    for (int o = 0; o < P.O; ++o) atomicAdd(&S.gpar[(1 + o) * P.C + c0 + i], S.priv[((1 + o) * TM_TPC + i) * blockDim.x + tid]);
+  }
+  __syncthreads();
+  for (int i = tid; i < n_par; i += blockDim.x) atomicAdd(i < P.C ? P.d_b1 + i : P.d_w2 + (i - P.C), S.gpar[i]);
 }
 
 }  // namespace pit

@@ -17,7 +17,7 @@ namespace launch {
 
 struct TallPlan {
   bool ok;
-  int cpl, l4, lanes4, chunks, rows_per_unit, grid, n_slots;
+  int cpl, l4, lanes4, chunks, rows_per_unit, grid, n_slots, threads;
   size_t smem;
 };
 
@@ -43,6 +43,7 @@ cudaError_t tail_forward(int geo, const TallPlan& plan, const TailParams& P, cud
 cudaError_t tail_backward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
 // tu_tail_mma_fwd.cu / tu_tail_mma_bwd.cu  (plan.rows_per_unit counts 16-row tiles per CTA)
 cudaError_t tail_mma_forward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
+cudaError_t tail_mma_backward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
 // tu_wide.cu
 int wide_pad(int width);
 cudaError_t wide_forward(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);

@@ -390,21 +390,54 @@ bool tail_mma_enabled() {
 
 bool tail_mma_eligible(const pit_problem_t* p, int out_dim) {
   const int c = p->dim;
-  return tail_mma_enabled() && tail_eligible(p, out_dim) && (c == 32 || c == 64 || c == 128) && ((int64_t)p->batch * c) % pit::TM_CHUNK == 0;
+  return tail_mma_enabled() && tail_eligible(p, out_dim) && (c == 32 || c == 64) && ((int64_t)p->batch * c) % pit::TM_CHUNK == 0;
 }
 
-TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
-  TallPlan c{};
-  if (!tail_mma_eligible(p, out_dim)) return c;
-  c.cpl = cpl_of(p->n_in);
-  c.smem = pit::tm_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim);
-  if (c.smem > (size_t)max_smem_optin() - 1024) return c;
+// rows_per_unit counts 16-row tiles per CTA; one 64-column chunk per warp, at most 8 warps
+void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c) {
+  const int chunks = p->batch * p->dim / pit::TM_CHUNK;
+  c.threads = chunks <= 4 ? 128 : 256;
   const int tiles = (p->n_out + pit::TM_ROWS - 1) / pit::TM_ROWS;
   const int target = sm_count() * 2;
   int per_cta = (tiles + target - 1) / target;
   per_cta = (per_cta + pit::TM_ROUND - 1) / pit::TM_ROUND * pit::TM_ROUND;
   c.rows_per_unit = per_cta;
   c.grid = (tiles + per_cta - 1) / per_cta;
+  c.cpl = cpl_of(p->n_in);
+}
+
+TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
+  TallPlan c{};
+  if (!tail_mma_eligible(p, out_dim)) return c;
+  plan_tail_mma_grid(p, c);
+  c.smem = pit::tm_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim);
+  if (c.smem > (size_t)max_smem_optin() - 1024) return c;
+  c.ok = true;
+  return c;
+}
+
+TallPlan plan_tail_mma_bwd(const pit_problem_t* p, int out_dim) {
+  TallPlan c{};
+  if (!tail_mma_eligible(p, out_dim)) return c;
+  plan_tail_mma_grid(p, c);
+  const int W = p->batch * p->dim;
+  const size_t fixed = pit::tm_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, 0, c.threads);
+  const size_t per_slot = (size_t)p->n_head * W * 4 + 2;
+  // two CTAs per SM if that leaves room for a useful slot set, else one
+  for (int per_sm = 2; per_sm >= 1; --per_sm) {
+    const size_t budget = ((size_t)max_smem_optin() + 1024) / per_sm - 2048;
+    if (budget <= fixed) continue;
+    int n = (int)((budget - fixed) / per_slot);
+    if (n > 64) n = 64;
+    if (n > p->n_in) n = p->n_in;
+    if (n >= 12 || n == p->n_in) {
+      c.n_slots = n;
+      break;
+    }
+  }
+  if (c.n_slots == 0) return c;
+  c.smem = pit::tm_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, c.n_slots, c.threads);
+  if (c.smem > (size_t)max_smem_optin() - 1024) return c;
   c.ok = true;
   return c;
 }
@@ -752,7 +785,8 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   if (!tail_eligible(p, out_dim)) return fail(PIT_ERR_ARG, "decoder tail: unsupported configuration (see pit_decoder_tail_supported)");
   if (!aligned16(y) || !aligned16(b1) || !aligned16(w2) || !aligned16(d_y) || !aligned16(d_b1) || !aligned16(d_w2))
     return fail(PIT_ERR_ARG, "decoder tail: y, b1, w2 and their gradients must be 16-byte aligned");
-  const TallPlan plan = plan_tail_bwd(p, out_dim);
+  const TallPlan mma = plan_tail_mma_bwd(p, out_dim);
+  const TallPlan plan = mma.ok ? mma : plan_tail_bwd(p, out_dim);
   if (!plan.ok) return fail(PIT_ERR_ARG, "decoder tail: no launch plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
@@ -769,7 +803,10 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   PIT_CUDA(cudaMemsetAsync(d_b1, 0, c * sizeof(float), st));
   PIT_CUDA(cudaMemsetAsync(d_w2, 0, (size_t)out_dim * c * sizeof(float), st));
   PIT_CUDA(cudaMemsetAsync(d_b2, 0, (size_t)out_dim * sizeof(float), st));
-  PIT_CUDA(launch::tail_backward(geo_of(p), plan, P, st));
+  if (mma.ok)
+    PIT_CUDA(launch::tail_mma_backward(geo_of(p), plan, P, st));
+  else
+    PIT_CUDA(launch::tail_backward(geo_of(p), plan, P, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }

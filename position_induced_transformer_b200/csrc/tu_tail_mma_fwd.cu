@@ -7,7 +7,7 @@ namespace launch {
 
 cudaError_t tail_mma_forward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st) {
   return with_geo(geo, plan.cpl, P.H, 1, [&](auto g, auto c, auto h, auto) {
-    return launch_smem(tail_mma_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value>, dim3(plan.grid), TALL_THREADS,
+    return launch_smem(tail_mma_fwd_kernel<decltype(g)::value, decltype(c)::value, decltype(h)::value>, dim3(plan.grid), plan.threads,
                        plan.smem, P, st);
   });
 }
