@@ -231,8 +231,10 @@ __host__ __device__ inline size_t tm_fwd_smem_bytes(int nh, int M, int C, int O)
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
-template <int GEO, int CPL, int NH>
+// NO: compile-time bound on out_dim -- 1 (the scalar-output models) or TAIL_MAX_OUT (any out_dim, decided at run time).
+template <int GEO, int CPL, int NH, int NO>
 __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(const TailParams P) {
+  const int n_out = NO == 1 ? 1 : P.O;
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TmTile<NH, false>;
   const size_t tile_stride = tm_align(sizeof(Tile));
@@ -247,9 +249,9 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
   for (int i = tid; i < P.C * (1 + P.O); i += blockDim.x) par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
-  float b2r[TAIL_MAX_OUT];
+  float b2r[NO];
 #pragma unroll
-  for (int o = 0; o < TAIL_MAX_OUT; ++o) b2r[o] = o < P.O ? __ldg(P.b2 + o) : 0.f;
+  for (int o = 0; o < NO; ++o) b2r[o] = o < n_out ? __ldg(P.b2 + o) : 0.f;
 
   const int chunks = P.B * P.C / TM_CHUNK;
   const int n_tiles = (P.N + TM_ROWS - 1) / TM_ROWS;
@@ -327,9 +329,9 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
         if (!active) continue;
         // epilogue: out[b, row, o] = b2[o] + sum_c W2[o, c] gelu(b1[c] + pre[c]); the thread holds channels c0..c0+TPC-1 of
         // rows 2t, 2t+1, 2t+8, 2t+9; the lanes of `group` consecutive g share the sample.
-        float part[TAIL_MAX_OUT][4];
+        float part[NO][4];
 #pragma unroll
-        for (int o = 0; o < TAIL_MAX_OUT; ++o)
+        for (int o = 0; o < NO; ++o)
 #pragma unroll
           for (int q = 0; q < 4; ++q) part[o][q] = 0.f;
 #pragma unroll
@@ -344,8 +346,8 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
 #pragma unroll
               for (int e = 0; e < 2; ++e) hid[nt * 2 + e] = tm_gelu(acc[mt][nt][half * 2 + e] + bias);
 #pragma unroll
-            for (int o = 0; o < TAIL_MAX_OUT; ++o) {
-              if (o < P.O) {
+            for (int o = 0; o < NO; ++o) {
+              if (o < n_out) {
                 const float wv = par[(1 + o) * P.C + c];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) part[o][q] = fmaf(wv, hid[q], part[o][q]);
@@ -354,14 +356,14 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
           }
         }
 #pragma unroll
-        for (int o = 0; o < TAIL_MAX_OUT; ++o) {
-          if (o >= P.O) break;
+        for (int o = 0; o < NO; ++o) {
+          if (o >= n_out) break;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float vsum = part[o][q];
             for (int off = 1; off < group; off <<= 1) vsum += __shfl_xor_sync(FULL, vsum, 4 * off);
             const int row = row0 + (q >> 1) * 8 + 2 * t + (q & 1);
-            if ((g % group) == 0 && row < P.N) P.out[((int64_t)b * P.N + row) * P.O + o] = vsum + b2r[o];
+            if ((g % group) == 0 && row < P.N) P.out[((int64_t)b * P.N + row) * n_out + o] = vsum + b2r[o];
           }
         }
       }
@@ -383,13 +385,14 @@ struct TmBwdSmem {
   int16_t* map;          // [M] column -> slot (-1: unbound)
   int16_t* slot_j;       // [n_slots]
   uint8_t* touched;      // [M]
-  int* ctl;
+  uint8_t* evict;        // [n_slots]
+  int* ctl;              // [0] columns needing a slot, [1] [2] free-slot bit masks, [3] bind counter
 };
 
 __host__ __device__ inline size_t tm_bwd_smem_bytes(int nh, int M, int W, int C, int O, int n_slots, int threads) {
   return TM_ROUND * (tm_tile_bytes(nh, true) + tm_cand_bytes(M)) + tm_align((size_t)n_slots * nh * W * 4) +
          tm_align((size_t)(1 + O) * TM_TPC * threads * 4) + 2 * tm_align((size_t)C * (1 + O) * 4) + 64 + tm_align((size_t)M * 2) +
-         tm_align((size_t)n_slots * 2) + tm_align(M) + 16;
+         tm_align((size_t)n_slots * 2) + tm_align(M) + tm_align(n_slots) + 16;
 }
 
 __device__ inline TmBwdSmem tm_bwd_carve(unsigned char* p, int nh, int M, int W, int C, int O, int n_slots, int threads) {
@@ -414,6 +417,8 @@ __device__ inline TmBwdSmem tm_bwd_carve(unsigned char* p, int nh, int M, int W,
   p += tm_align((size_t)n_slots * 2);
   s.touched = reinterpret_cast<uint8_t*>(p);
   p += tm_align(M);
+  s.evict = reinterpret_cast<uint8_t*>(p);
+  p += tm_align(n_slots);
   s.ctl = reinterpret_cast<int*>(p);
   return s;
 }
@@ -422,25 +427,85 @@ __device__ inline TmBwdSmem tm_bwd_carve(unsigned char* p, int nh, int M, int W,
 // the four lanes of a quad, which address four different slots at the same column, fall into different banks.
 __device__ __forceinline__ int tm_slot_pos(int x, int sidx) { return (x & ~31) | ((x + 4 * (sidx & 7)) & 31); }
 
-// Flush every bound slot into d_y with vector REDs and clear it.  Cells are split over the CTA's threads.
+// Flush one slot into d_y with vector REDs and clear it; the cells are split over the CTA's threads.
 template <int NH>
-__device__ __forceinline__ void tm_flush_slots(const TailParams& P, const TmBwdSmem& S, int W) {
-  const int used = min(S.ctl[0], P.n_slots);
-  const int w4 = W / 4;
-  for (int i = threadIdx.x; i < used * NH * w4; i += blockDim.x) {
-    const int sidx = i / (NH * w4);
-    const int rem = i - sidx * (NH * w4);
-    const int h = rem / w4, x = (rem - h * w4) * 4;
-    float4* cell = reinterpret_cast<float4*>(S.slot_acc + ((size_t)sidx * NH + h) * W + tm_slot_pos(x, sidx));
-    const int b = x / P.C, c = x - b * P.C;
-    const int j = S.slot_j[sidx];
-    atomicAdd(reinterpret_cast<float4*>(P.d_y + (((size_t)b * P.M + j) * NH + h) * P.C + c), *cell);
-    *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ void tm_flush_slot(const TailParams& P, const TmBwdSmem& S, int W, int log2c, int sidx) {
+  const int j = S.slot_j[sidx];
+  for (int h = 0; h < NH; ++h) {
+    for (int x = 4 * threadIdx.x; x < W; x += 4 * blockDim.x) {
+      float4* cell = reinterpret_cast<float4*>(S.slot_acc + ((size_t)sidx * NH + h) * W + tm_slot_pos(x, sidx));
+      const int b = x >> log2c, c = x & (P.C - 1);
+      atomicAdd(reinterpret_cast<float4*>(P.d_y + (((size_t)b * P.M + j) * NH + h) * P.C + c), *cell);
+      *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
-template <int GEO, int CPL, int NH>
+// Bit masks of the free slots (slot_j < 0), computed by warp 0 into ctl[1], ctl[2] (n_slots <= 64).
+__device__ __forceinline__ void tm_free_masks(const TailParams& P, const TmBwdSmem& S, int lane) {
+  const unsigned m0 = __ballot_sync(FULL, lane < P.n_slots && S.slot_j[min(lane, P.n_slots - 1)] < 0);
+  const unsigned m1 = __ballot_sync(FULL, lane + 32 < P.n_slots && S.slot_j[min(lane + 32, P.n_slots - 1)] < 0);
+  if (lane == 0) {
+    S.ctl[1] = (int)m0;
+    S.ctl[2] = (int)m1;
+  }
+}
+
+// Slot management of one round, called by the whole CTA after phase 1 has marked the candidate columns in
+// S.touched: every touched column without a slot gets a free one; if there are not enough, the slots of columns
+// NOT touched in this round are flushed and recycled first (the candidate window slides along the mesh, so these
+// are the columns left behind); whatever is still unbound afterwards goes to d_y with direct REDs.
+template <int NH>
+__device__ __forceinline__ void tm_bind_slots(const TailParams& P, const TmBwdSmem& S, int W, int log2c) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) tm_free_masks(P, S, lane);
+  for (int j = tid; j < P.M; j += blockDim.x)
+    if (S.touched[j] && S.map[j] < 0) atomicAdd(&S.ctl[0], 1);
+  __syncthreads();
+  if (S.ctl[0] > __popc((unsigned)S.ctl[1]) + __popc((unsigned)S.ctl[2])) {  // CTA-uniform
+    for (int sidx = tid; sidx < P.n_slots; sidx += blockDim.x) S.evict[sidx] = S.slot_j[sidx] >= 0 && !S.touched[S.slot_j[sidx]];
+    __syncthreads();
+    for (int sidx = 0; sidx < P.n_slots; ++sidx)
+      if (S.evict[sidx]) tm_flush_slot<NH>(P, S, W, log2c, sidx);
+    __syncthreads();
+    for (int sidx = tid; sidx < P.n_slots; sidx += blockDim.x) {
+      if (S.evict[sidx]) {
+        S.map[S.slot_j[sidx]] = -1;
+        S.slot_j[sidx] = -1;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) tm_free_masks(P, S, lane);
+    __syncthreads();
+  }
+  const unsigned m0 = (unsigned)S.ctl[1], m1 = (unsigned)S.ctl[2];
+  const int n0 = __popc(m0), n1 = __popc(m1);
+  for (int j = tid; j < P.M; j += blockDim.x) {
+    if (S.touched[j] && S.map[j] < 0) {
+      const int k = atomicAdd(&S.ctl[3], 1);
+      int sidx = -1;
+      if (k < n0)
+        sidx = (int)__fns(m0, 0, k + 1);
+      else if (k < n0 + n1)
+        sidx = 32 + (int)__fns(m1, 0, k - n0 + 1);
+      if (sidx >= 0) {
+        S.map[j] = (int16_t)sidx;
+        S.slot_j[sidx] = (int16_t)j;
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < P.M; j += blockDim.x) S.touched[j] = 0;
+  if (tid == 0) {
+    S.ctl[0] = 0;
+    S.ctl[3] = 0;
+  }
+  // the caller's next __syncthreads (end of the round) orders these resets before the next phase 1
+}
+
+template <int GEO, int CPL, int NH, int NO>
 __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(const TailParams P) {
+  const int n_out = NO == 1 ? 1 : P.O;
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TmTile<NH, true>;
   const int W = P.B * P.C;
@@ -465,18 +530,20 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
   }
   for (int i = tid; i < P.n_slots * NH * W; i += blockDim.x) S.slot_acc[i] = 0.f;
   for (int i = 0; i < (1 + P.O) * TM_TPC; ++i) S.priv[i * blockDim.x + tid] = 0.f;
-  if (tid == 0) {
-    S.ctl[0] = 0;
-    S.ctl[1] = 0;
+  for (int i = tid; i < P.n_slots; i += blockDim.x) {
+    S.slot_j[i] = -1;
+    S.evict[i] = 0;
   }
+  if (tid < 4) S.ctl[tid] = 0;
+  const int log2c = 31 - __clz(P.C);
   __syncthreads();
 
   float ds_head[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) ds_head[h] = 0.f;
-  float db2[TAIL_MAX_OUT];
+  float db2[NO];
 #pragma unroll
-  for (int o = 0; o < TAIL_MAX_OUT; ++o) db2[o] = 0.f;
+  for (int o = 0; o < NO; ++o) db2[o] = 0.f;
 
   const int chunks = W / TM_CHUNK;
   const int n_tiles = (P.N + TM_ROWS - 1) / TM_ROWS;
@@ -518,40 +585,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
       if (lane == 0) T->cnt = cnt;
     }
     __syncthreads();
-    // bind a slot to every column touched in this round; flush everything once if the set is full
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      for (int j = tid; j < P.M; j += blockDim.x) {
-        if (S.touched[j] && S.map[j] < 0) {
-          const int sidx = atomicAdd(&S.ctl[0], 1);
-          if (sidx < P.n_slots) {
-            S.map[j] = (int16_t)sidx;
-            S.slot_j[sidx] = (int16_t)j;
-          } else {
-            S.ctl[1] = 1;
-          }
-        }
-      }
-      __syncthreads();
-      const bool overflow = S.ctl[1] != 0;
-      __syncthreads();  // every thread has read the flag before thread 0 may reset it
-      if (!overflow) break;
-      if (attempt == 0) {
-        tm_flush_slots<NH>(P, S, W);
-        __syncthreads();
-        for (int j = tid; j < P.M; j += blockDim.x) S.map[j] = -1;
-        if (tid == 0) {
-          S.ctl[0] = 0;
-          S.ctl[1] = 0;
-        }
-        __syncthreads();
-      } else {
-        if (tid == 0) {
-          S.ctl[0] = P.n_slots;
-          S.ctl[1] = 0;
-        }
-      }
-    }
-    for (int j = tid; j < P.M; j += blockDim.x) S.touched[j] = 0;
+    tm_bind_slots<NH>(P, S, W, log2c);
     __syncthreads();
     // ---- phase 2 ----
     for (int v = 0; v < in_round; ++v) {
@@ -590,13 +624,13 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
         }
         // (b) g1 = gelu'(pre) * (W2^T dOut[b, row, :]) in place; parameter-gradient partials
         if (active) {
-          float go[4][TAIL_MAX_OUT];
+          float go[4][NO];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int row = row0 + (q >> 1) * 8 + 2 * t + (q & 1);
 #pragma unroll
-            for (int o = 0; o < TAIL_MAX_OUT; ++o) {
-              go[q][o] = (o < P.O && row < P.N) ? __ldg(P.d_out + ((int64_t)b * P.N + row) * P.O + o) : 0.f;
+            for (int o = 0; o < NO; ++o) {
+              go[q][o] = (o < n_out && row < P.N) ? __ldg(P.d_out + ((int64_t)b * P.N + row) * n_out + o) : 0.f;
               if ((g % group) == 0) db2[o] += go[q][o];
             }
           }
@@ -607,10 +641,10 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
               const int i = 2 * mt + half;
               const int c = c0 + i;
               const float bias = S.par[c];
-              float wv[TAIL_MAX_OUT], dw[TAIL_MAX_OUT];
+              float wv[NO], dw[NO];
 #pragma unroll
-              for (int o = 0; o < TAIL_MAX_OUT; ++o) {
-                wv[o] = o < P.O ? S.par[(1 + o) * P.C + c] : 0.f;
+              for (int o = 0; o < NO; ++o) {
+                wv[o] = o < n_out ? S.par[(1 + o) * P.C + c] : 0.f;
                 dw[o] = 0.f;
               }
               float gsum = 0.f;
@@ -620,8 +654,8 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
                 tm_gelu_pair(acc[mt][q >> 1][half * 2 + (q & 1)] + bias, hid, dhid);
                 float up = 0.f;
 #pragma unroll
-                for (int o = 0; o < TAIL_MAX_OUT; ++o) {
-                  if (o < P.O) {
+                for (int o = 0; o < NO; ++o) {
+                  if (o < n_out) {
                     up = fmaf(go[q][o], wv[o], up);
                     dw[o] = fmaf(go[q][o], hid, dw[o]);
                   }
@@ -632,8 +666,8 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
               }
               S.priv[i * blockDim.x + tid] += gsum;
 #pragma unroll
-              for (int o = 0; o < TAIL_MAX_OUT; ++o)
-                if (o < P.O) S.priv[((1 + o) * TM_TPC + i) * blockDim.x + tid] += dw[o];
+              for (int o = 0; o < NO; ++o)
+                if (o < n_out) S.priv[((1 + o) * TM_TPC + i) * blockDim.x + tid] += dw[o];
             }
           }
         }
@@ -735,7 +769,8 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
     }
     __syncthreads();
   }
-  tm_flush_slots<NH>(P, S, W);
+  for (int sidx = 0; sidx < P.n_slots; ++sidx)
+    if (S.slot_j[sidx] >= 0) tm_flush_slot<NH>(P, S, W, log2c, sidx);
 
   // ---- parameter gradients: one reduction per CTA ----
 #pragma unroll
@@ -751,8 +786,8 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
     }
   }
 #pragma unroll
-  for (int o = 0; o < TAIL_MAX_OUT; ++o) {
-    if (o >= P.O) continue;  // uniform
+  for (int o = 0; o < NO; ++o) {
+    if (o >= n_out) continue;  // uniform
     const float v = warp_sum(db2[o]);
     __syncthreads();
     if (lane == 0) S.red[warp] = v;
