@@ -12,14 +12,15 @@
 // (bit-exact d2, per-head cut, fp32 weights); only the products are split:  hi*hi + lo*hi + hi*lo with fp32
 // accumulation (error ~2^-21, inside the 1e-5 parity budget).
 //
-// Work split.  A CTA (4 or 8 warps) walks its tiles in rounds of 4:
-//   phase 1  warp w < 4 "prepares" tile w of the round: scans the M columns held in registers against the 16 rows
-//            (head-independent d2-space pre-filter), ballot-compacts the candidate list, evaluates the unnormalised
-//            weights P[h][row][cand] (and d2) into a shared-memory block, and the row sums;
+// Work split.  A CTA (4 or 8 warps) walks its tiles in rounds (forward: one tile per warp, backward: 4):
+//   phase 1  warp w "prepares" tile w of the round: scans the M columns held in registers against the 16 rows
+//            (head-independent d2-space pre-filter, behind a bounding-box test per 32 columns), ballot-compacts the
+//            candidate list, evaluates the normalised weights P^[h][row][cand] (backward: also P^ (d2 - m)) into a
+//            shared-memory block, and the row sums;
 //   phase 2  for every prepared tile, warp w owns the 64-column chunk(s) w, w+nwarps, ... of the B*C-wide hidden
 //            vector: operand A = Y^T straight from global/L1 (a thread reads 8 contiguous floats of two candidate
 //            rows; the column order inside an m16 tile is permuted so that a fragment is two 64-bit loads),
-//            operand B = P^T from the shared block (conflict-free with the 36-float pitch), accumulators
+//            operand B = P^T from the shared block (conflict-free with the 20-float pitch), accumulators
 //            [64 cols x 16 rows] in 32 registers; epilogue = bias + exact GELU + C->O projection on the fragments.
 // The transposed orientation (columns on the MMA m axis, rows on n) is what makes the backward cheap: the
 // accumulator fragment of g1^T is, register for register, the A fragment of dY^T = g1^T . P (reduction over rows),
@@ -28,7 +29,7 @@
 // dY is accumulated without atomics in shared-memory slots bound to latent columns (one owner thread per cell), as
 // in tall_bwd_kernel, and flushed with vector REDs.
 //
-// Tiles whose candidate list exceeds one 32-column block (incoherent meshes, unmasked decoders) are handled by
+// Tiles whose candidate list exceeds one 16-column block (incoherent meshes, unmasked decoders) are handled by
 // recomputing further blocks on the fly -- slower, same results.
 #pragma once
 #include "decoder_tail.cuh"
@@ -36,13 +37,13 @@
 namespace pit {
 
 constexpr int TM_ROWS = 16;   // rows per tile (two n8 MMA tiles)
-constexpr int TM_KT = 32;     // candidates per weight block
-constexpr int TM_LD = 36;     // pitch of a block row in floats: fragment reads hit 32 distinct banks
+constexpr int TM_KT = 16;     // candidates per weight block (99.8 % of the Darcy-421 tiles have <= 16)
+constexpr int TM_LD = 20;     // pitch of a block row in floats: fragment reads hit 32 distinct banks
 constexpr int TM_MT = 4;      // m16 MMA tiles per warp pass
 constexpr int TM_CHUNK = 16 * TM_MT;  // hidden-vector columns per warp pass
 constexpr int TM_TPC = 2 * TM_MT;     // contiguous columns a thread owns inside a chunk
-constexpr int TM_ROUND = 4;   // tiles prepared per round (one per warp 0..3)
 constexpr int TM_MAX_WARPS = 8;
+constexpr int TM_BWD_ROUND = 4;  // tiles prepared per round in the backward (warps 0..3): keeps shared memory for dY slots
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -105,10 +106,36 @@ __device__ __forceinline__ TmRow<GEO, NH> tm_row(const TailParams& P, int row, c
   return R;
 }
 
+__device__ __forceinline__ float tm_warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ float tm_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
 // Candidate list of a tile: every column within the pre-filter radius of at least one of its rows, in column order.
+// Euclidean geometries first test each column against the tile's bounding box inflated by the largest radius; a
+// group of 32 columns (one per lane) in which no lane passes skips the 16 exact row tests.
 template <int GEO, int CPL, int NH>
 __device__ __forceinline__ int tm_candidates(const TmRow<GEO, NH>& R, const Point<GEO> (&col)[CPL], int M, int lane, float period,
                                              int16_t* cand) {
+  uint32_t groups = 0xffffffffu;
+  if (GEO == GEO_EUCLID1 || GEO == GEO_EUCLID2) {
+    const float x0 = tm_warp_min(R.o.x), x1 = tm_warp_max(R.o.x);
+    const float y0 = GEO == GEO_EUCLID2 ? tm_warp_min(R.o.y) : 0.f, y1 = GEO == GEO_EUCLID2 ? tm_warp_max(R.o.y) : 0.f;
+    const float reach = tm_warp_max(R.vcap) * 1.0001f;  // slack for the different rounding of the box distance
+    groups = 0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const float dx = fmaxf(fmaxf(x0 - col[c].x, col[c].x - x1), 0.f);
+      const float dy = GEO == GEO_EUCLID2 ? fmaxf(fmaxf(y0 - col[c].y, col[c].y - y1), 0.f) : 0.f;
+      if (__any_sync(FULL, fmaf(dx, dx, dy * dy) <= reach)) groups |= 1u << c;
+    }
+  }
   uint32_t flags = 0;
   for (int i = 0; i < TM_ROWS; ++i) {
     Point<GEO> o;
@@ -116,12 +143,14 @@ __device__ __forceinline__ int tm_candidates(const TmRow<GEO, NH>& R, const Poin
     o.y = __shfl_sync(FULL, R.o.y, i);
     const float vc = __shfl_sync(FULL, R.vcap, i);
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) flags |= (dist2<GEO>(o, col[c], period) <= vc) ? (1u << c) : 0u;
+    for (int c = 0; c < CPL; ++c)
+      if ((groups >> c) & 1u) flags |= (dist2<GEO>(o, col[c], period) <= vc) ? (1u << c) : 0u;  // warp-uniform branch
   }
   int n = 0;
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
+    if (!((groups >> c) & 1u)) continue;
     const int j = c * 32 + lane;
     const bool f = ((flags >> c) & 1u) && j < M;
     const unsigned m = __ballot_sync(FULL, f);
@@ -132,12 +161,14 @@ __device__ __forceinline__ int tm_candidates(const TmRow<GEO, NH>& R, const Poin
   return n;
 }
 
-// One block (<= 32 candidates, zero-filled to the next multiple of 8) of unnormalised weights:
-// lane -> (row lane&15, candidates of parity lane>>4).  pt = [NH][16][TM_LD], d2t = [16][TM_LD] or null.
+// One block (<= 16 candidates, zero-filled to the next multiple of 8) of weights scaled by post[h]:
+// lane -> (row lane&15, candidates of parity lane>>4).  pt = [NH][16][TM_LD]; zt (backward) = [NH][16][TM_LD], of which
+// plane 0 receives d2 here and tm_block_finish turns all planes into P^ (d2 - m).
+// psum / pdsum accumulate post*p and post*p*d2 of this lane's entries.
 template <int GEO, int NH>
 __device__ __forceinline__ void tm_block(const TailParams& P, const TmRow<GEO, NH>& R, const float (&s)[NH], float period,
-                                         const int16_t* cand, int cnt, int kb, int lane, float* pt, float* d2t, float (&psum)[NH],
-                                         float (&pdsum)[NH]) {
+                                         const int16_t* cand, int cnt, int kb, int lane, float* pt, float* zt, const float (&post)[NH],
+                                         float (&psum)[NH], float (&pdsum)[NH]) {
   const int i = lane & 15;
   const int base = kb * TM_KT;
   const int kmax = min(TM_KT, (cnt - base + 7) & ~7);
@@ -151,43 +182,77 @@ __device__ __forceinline__ void tm_block(const TailParams& P, const TmRow<GEO, N
       float p = 0.f;
       if (live) {
         const float sc = __fmul_rn(d2, s[h]);
-        if (sc <= R.cut[h]) p = __expf(__fsub_rn(R.top[h], sc));
+        if (sc <= R.cut[h]) p = __expf(__fsub_rn(R.top[h], sc)) * post[h];
       }
       psum[h] += p;
       pdsum[h] = fmaf(p, d2, pdsum[h]);
       pt[(h * TM_ROWS + i) * TM_LD + k] = p;
     }
-    if (d2t) d2t[i * TM_LD + k] = live ? d2 : 0.f;
+    if (zt) zt[i * TM_LD + k] = live ? d2 : 0.f;
+  }
+}
+// Second pass over the entries this lane wrote: forward scales by 1/l (zt == null), backward forms P^ (d2 - m_h).
+template <int NH>
+__device__ __forceinline__ void tm_block_finish(int cnt, int kb, int lane, float* pt, float* zt, const float (&inv_l)[NH],
+                                                const float (&m)[NH]) {
+  const int i = lane & 15;
+  const int kmax = min(TM_KT, (cnt - kb * TM_KT + 7) & ~7);
+  for (int k = lane >> 4; k < kmax; k += 2) {
+    if (zt) {
+      const float d2 = zt[i * TM_LD + k];
+#pragma unroll
+      for (int h = NH - 1; h >= 0; --h) zt[(h * TM_ROWS + i) * TM_LD + k] = pt[(h * TM_ROWS + i) * TM_LD + k] * (d2 - m[h]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < NH; ++h) pt[(h * TM_ROWS + i) * TM_LD + k] *= inv_l[h];
+    }
   }
 }
 
 // Shared-memory image of a prepared tile.
 template <int NH, bool BWD>
 struct TmTile {
-  float p[NH][TM_ROWS][TM_LD];         // unnormalised weights of block 0 (or of the block being processed)
-  float d2[BWD ? TM_ROWS : 1][TM_LD];  // squared distances (backward only)
-  float inv_l[NH][TM_ROWS];            // 1 / row sum (0 for rows past the end)
-  float m[NH][TM_ROWS];                // backward: sum_j P^ d2
+  float p[NH][TM_ROWS][TM_LD];             // normalised weights P^ of block 0 (or of the block being processed)
+  float z[BWD ? NH : 1][BWD ? TM_ROWS : 1][TM_LD];  // backward: P^ (d2 - m)
+  float inv_l[NH][TM_ROWS];                // 1 / row sum (0 for rows past the end)
+  float m[NH][TM_ROWS];                    // backward: sum_j P^ d2
   int cnt;
   int pad[3];
 };
 
-// pre^T += Y_h^T . P_h^T for one block of one tile and one 64-column chunk.
+// Rebuild block kb of a prepared tile in place (candidate lists longer than one block); one warp.
+template <int GEO, int NH, bool BWD>
+__device__ __forceinline__ void tm_rebuild(const TailParams& P, TmTile<NH, BWD>* T, const int16_t* cand, int row0, int kb, int lane,
+                                           const float (&s)[NH], float period) {
+  const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row0 + (lane & 15), s);
+  float inv[NH], m[NH], ps[NH], pd[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    inv[h] = T->inv_l[h][lane & 15];
+    m[h] = T->m[h][lane & 15];
+    ps[h] = pd[h] = 0.f;
+  }
+  tm_block<GEO, NH>(P, R, s, period, cand, T->cnt, kb, lane, &T->p[0][0][0], BWD ? &T->z[0][0][0] : nullptr, inv, ps, pd);
+  if (BWD) tm_block_finish<NH>(T->cnt, kb, lane, &T->p[0][0][0], &T->z[0][0][0], inv, m);
+}
+
+// pre^T += Y_h^T . P^_h^T for one block of one tile and one 64-column chunk.
 //   acc[mt][nt][e]: chunk column TPC*g + 2*mt + (e >> 1), tile row 8*nt + 2*t + (e & 1).
 // y_chunk points at Y[b, 0, 0, c] for this thread's TPC columns; row j of head h sits (NH*j + h)*C floats further.
 template <int NH>
-__device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const float (*p)[TM_ROWS][TM_LD], const float (*inv_l)[TM_ROWS],
-                                             const int16_t* cand, int cnt, int kb, const float* y_chunk, int C, int g, int t) {
+__device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const float (*p)[TM_ROWS][TM_LD], const int16_t* cand, int cnt,
+                                             int kb, const float* y_chunk, int C, int g, int t) {
   const int base = kb * TM_KT;
   const int ksteps = (min(cnt - base, TM_KT) + 7) >> 3;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int ka = base + ks * 8 + t, kc = ka + 4;
+    const int ja = ka < cnt ? (int)cand[ka] : 0, jb = kc < cnt ? (int)cand[kc] : 0;
+    const float* ra0 = y_chunk + (size_t)ja * NH * C;
+    const float* rb0 = y_chunk + (size_t)jb * NH * C;
 #pragma unroll
-  for (int h = 0; h < NH; ++h) {
-    const float inv0 = inv_l[h][g], inv1 = inv_l[h][g + 8];
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const int ka = base + ks * 8 + t, kc = ka + 4;
-      const int ja = ka < cnt ? (int)cand[ka] : 0, jb = kc < cnt ? (int)cand[kc] : 0;
-      const float2* ra = reinterpret_cast<const float2*>(y_chunk + ((size_t)ja * NH + h) * C);
-      const float2* rb = reinterpret_cast<const float2*>(y_chunk + ((size_t)jb * NH + h) * C);
+    for (int h = 0; h < NH; ++h) {
+      const float2* ra = reinterpret_cast<const float2*>(ra0 + h * C);
+      const float2* rb = reinterpret_cast<const float2*>(rb0 + h * C);
       float2 ya[TM_MT], yb[TM_MT];
 #pragma unroll
       for (int mt = 0; mt < TM_MT; ++mt) {
@@ -197,8 +262,7 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const fl
       uint32_t bh[2][2], bl[2][2];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        const float inv = nt == 0 ? inv0 : inv1;
-        const float p0 = p[h][g + 8 * nt][ks * 8 + t] * inv, p1 = p[h][g + 8 * nt][ks * 8 + t + 4] * inv;
+        const float p0 = p[h][g + 8 * nt][ks * 8 + t], p1 = p[h][g + 8 * nt][ks * 8 + t + 4];
         const float h0 = tm_round_hi(p0), h1 = tm_round_hi(p1);
         bh[nt][0] = __float_as_uint(h0), bh[nt][1] = __float_as_uint(h1);
         bl[nt][0] = __float_as_uint(p0 - h0), bl[nt][1] = __float_as_uint(p1 - h1);
@@ -224,8 +288,8 @@ __host__ __device__ inline size_t tm_tile_bytes(int nh, bool bwd) {
   return nh == 1 ? (bwd ? tm_align(sizeof(TmTile<1, true>)) : tm_align(sizeof(TmTile<1, false>)))
                  : (bwd ? tm_align(sizeof(TmTile<2, true>)) : tm_align(sizeof(TmTile<2, false>)));
 }
-__host__ __device__ inline size_t tm_fwd_smem_bytes(int nh, int M, int C, int O) {
-  return 2 * TM_ROUND * (tm_tile_bytes(nh, false) + tm_cand_bytes(M)) + tm_align((size_t)C * (1 + O) * 4);
+__host__ __device__ inline size_t tm_fwd_smem_bytes(int nh, int M, int C, int O, int threads) {
+  return 2 * (threads / 32) * (tm_tile_bytes(nh, false) + tm_cand_bytes(M)) + tm_align((size_t)C * (1 + O) * 4);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -237,18 +301,18 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
   const int n_out = NO == 1 ? 1 : P.O;
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TmTile<NH, false>;
-  const size_t tile_stride = tm_align(sizeof(Tile));
-  unsigned char* cand_base = tall_smem_raw + 2 * TM_ROUND * tile_stride;
-  const size_t cand_stride = tm_cand_bytes(P.M);
-  float* par = reinterpret_cast<float*>(cand_base + 2 * TM_ROUND * cand_stride);  // [b1 (C) | W2 (O x C)]
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const size_t tile_stride = tm_align(sizeof(Tile));
+  unsigned char* cand_base = tall_smem_raw + 2 * nwarps * tile_stride;
+  const size_t cand_stride = tm_cand_bytes(P.M);
+  float* par = reinterpret_cast<float*>(cand_base + 2 * nwarps * cand_stride);  // [b1 (C) | W2 (O x C)]
+
   const int g = lane >> 2, t = lane & 3;
   const float period = P.period ? __ldg(P.period) : 0.f;
   float s[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
-  for (int i = tid; i < P.C * (1 + P.O); i += blockDim.x) par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
+  for (int i = tid; i < P.C * (1 + n_out); i += blockDim.x) par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
   float b2r[NO];
 #pragma unroll
   for (int o = 0; o < NO; ++o) b2r[o] = o < n_out ? __ldg(P.b2 + o) : 0.f;
@@ -260,10 +324,10 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
   const int c0 = (TM_TPC * g) % P.C;  // this thread's hidden channels (the same in every chunk: C divides the chunk width)
   const int group = P.C / TM_TPC;     // consecutive g sharing a sample
   int round = 0;
-  for (int tb = tile_begin; tb < tile_end; tb += TM_ROUND, ++round) {
-    const int in_round = min(TM_ROUND, tile_end - tb);
-    const int set = (round & 1) * TM_ROUND;
-    // ---- phase 1: one tile per warp (warps 0..3) ----
+  for (int tb = tile_begin; tb < tile_end; tb += nwarps, ++round) {
+    const int in_round = min(nwarps, tile_end - tb);
+    const int set = (round & 1) * nwarps;
+    // ---- phase 1: one tile per warp ----
     if (warp < in_round) {
       Point<GEO> col[CPL];
 #pragma unroll
@@ -276,20 +340,26 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
       const int row = (tb + warp) * TM_ROWS + (lane & 15);
       const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row, s);
       const int cnt = tm_candidates<GEO, CPL, NH>(R, col, P.M, lane, period, cand);
-      float psum[NH], pdsum[NH];
+      float psum[NH], pdsum[NH], one[NH], inv[NH];
 #pragma unroll
-      for (int h = 0; h < NH; ++h) psum[h] = pdsum[h] = 0.f;
+      for (int h = 0; h < NH; ++h) {
+        psum[h] = pdsum[h] = 0.f;
+        one[h] = 1.f;
+      }
       const int nkb = (cnt + TM_KT - 1) / TM_KT;
       for (int kb = nkb - 1; kb >= 0; --kb)  // block 0 last: it is the one left in the tile for phase 2
-        tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], nullptr, psum, pdsum);
+        tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], nullptr, one, psum, pdsum);
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         const float l = psum[h] + __shfl_xor_sync(FULL, psum[h], 16);
+        inv[h] = R.valid ? 1.f / l : 0.f;
         if (lane < TM_ROWS) {
-          T->inv_l[h][lane] = R.valid ? 1.f / l : 0.f;
+          T->inv_l[h][lane] = inv[h];
+          T->m[h][lane] = 0.f;
           if (R.valid) P.rowsum[(int64_t)h * P.N + row] = l;
         }
       }
+      if (nkb > 0) tm_block_finish<NH>(cnt, 0, lane, &T->p[0][0][0], nullptr, inv, inv);
       if (lane == 0) T->cnt = cnt;
     }
     __syncthreads();
@@ -315,16 +385,10 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
         for (int kb = 0; kb < nkb; ++kb) {
           if (nkb > 1) {  // rare: the candidate list spans several blocks -> rebuild block kb in place (CTA-uniform branch)
             __syncthreads();
-            if (warp == 0) {
-              const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row0 + (lane & 15), s);
-              float ps[NH], pd[NH];
-#pragma unroll
-              for (int h = 0; h < NH; ++h) ps[h] = pd[h] = 0.f;
-              tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], nullptr, ps, pd);
-            }
+            if (warp == 0) tm_rebuild<GEO, NH, false>(P, T, cand, row0, kb, lane, s, period);
             __syncthreads();
           }
-          if (active) tm_mma_block<NH>(acc, T->p, T->inv_l, cand, cnt, kb, y_chunk, P.C, g, t);
+          if (active) tm_mma_block<NH>(acc, T->p, cand, cnt, kb, y_chunk, P.C, g, t);
         }
         if (!active) continue;
         // epilogue: out[b, row, o] = b2[o] + sum_c W2[o, c] gelu(b1[c] + pre[c]); the thread holds channels c0..c0+TPC-1 of
@@ -375,22 +439,22 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
 // backward
 // ---------------------------------------------------------------------------------------
 struct TmBwdSmem {
-  unsigned char* tiles;  // [TM_ROUND] TmTile<NH, true>
-  unsigned char* cand;   // [TM_ROUND][M] int16
+  unsigned char* tiles;  // [TM_BWD_ROUND] TmTile<NH, true>
+  unsigned char* cand;   // [TM_BWD_ROUND][M] int16
   float* slot_acc;       // [n_slots][NH][W], columns rotated inside 32-float windows by 4*(slot & 7)
   float* priv;           // [(1+O)*TPC][threads]: per-thread partial sums of d_b1 and d_w2 for its channels
   float* par;            // [C + O*C]: b1 then W2
   float* gpar;           // [C + O*C]: CTA-level reduction of d_b1, d_w2
   float* red;            // [TM_MAX_WARPS]
   int16_t* map;          // [M] column -> slot (-1: unbound)
-  int16_t* slot_j;       // [n_slots]
+  int16_t* slot_j;       // [n_slots] slot -> column (-1: free)
   uint8_t* touched;      // [M]
   uint8_t* evict;        // [n_slots]
   int* ctl;              // [0] columns needing a slot, [1] [2] free-slot bit masks, [3] bind counter
 };
 
 __host__ __device__ inline size_t tm_bwd_smem_bytes(int nh, int M, int W, int C, int O, int n_slots, int threads) {
-  return TM_ROUND * (tm_tile_bytes(nh, true) + tm_cand_bytes(M)) + tm_align((size_t)n_slots * nh * W * 4) +
+  return TM_BWD_ROUND * (tm_tile_bytes(nh, true) + tm_cand_bytes(M)) + tm_align((size_t)n_slots * nh * W * 4) +
          tm_align((size_t)(1 + O) * TM_TPC * threads * 4) + 2 * tm_align((size_t)C * (1 + O) * 4) + 64 + tm_align((size_t)M * 2) +
          tm_align((size_t)n_slots * 2) + tm_align(M) + tm_align(n_slots) + 16;
 }
@@ -398,9 +462,9 @@ __host__ __device__ inline size_t tm_bwd_smem_bytes(int nh, int M, int W, int C,
 __device__ inline TmBwdSmem tm_bwd_carve(unsigned char* p, int nh, int M, int W, int C, int O, int n_slots, int threads) {
   TmBwdSmem s{};
   s.tiles = p;
-  p += TM_ROUND * tm_tile_bytes(nh, true);
+  p += TM_BWD_ROUND * tm_tile_bytes(nh, true);
   s.cand = p;
-  p += TM_ROUND * tm_cand_bytes(M);
+  p += TM_BWD_ROUND * tm_cand_bytes(M);
   s.slot_acc = reinterpret_cast<float*>(p);
   p += tm_align((size_t)n_slots * nh * W * 4);
   s.priv = reinterpret_cast<float*>(p);
@@ -509,7 +573,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TmTile<NH, true>;
   const int W = P.B * P.C;
-  const TmBwdSmem S = tm_bwd_carve(tall_smem_raw, NH, P.M, W, P.C, P.O, P.n_slots, blockDim.x);
+  const TmBwdSmem S = tm_bwd_carve(tall_smem_raw, NH, P.M, W, P.C, n_out, P.n_slots, blockDim.x);
   const size_t tile_stride = tm_align(sizeof(Tile));
   const size_t cand_stride = tm_cand_bytes(P.M);
 
@@ -519,7 +583,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
   float s[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
-  const int n_par = P.C * (1 + P.O);
+  const int n_par = P.C * (1 + n_out);
   for (int i = tid; i < n_par; i += blockDim.x) {
     S.par[i] = i < P.C ? __ldg(P.b1 + i) : __ldg(P.w2 + (i - P.C));
     S.gpar[i] = 0.f;
@@ -529,7 +593,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
     S.touched[j] = 0;
   }
   for (int i = tid; i < P.n_slots * NH * W; i += blockDim.x) S.slot_acc[i] = 0.f;
-  for (int i = 0; i < (1 + P.O) * TM_TPC; ++i) S.priv[i * blockDim.x + tid] = 0.f;
+  for (int i = 0; i < (1 + n_out) * TM_TPC; ++i) S.priv[i * blockDim.x + tid] = 0.f;
   for (int i = tid; i < P.n_slots; i += blockDim.x) {
     S.slot_j[i] = -1;
     S.evict[i] = 0;
@@ -551,9 +615,9 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
   const int tile_end = min(n_tiles, tile_begin + P.rows_per_unit);
   const int c0 = (TM_TPC * g) % P.C;
   const int group = P.C / TM_TPC;
-  for (int tb = tile_begin; tb < tile_end; tb += TM_ROUND) {
-    const int in_round = min(TM_ROUND, tile_end - tb);
-    // ---- phase 1: one tile per warp (warps 0..3): candidates, weights, d2, 1/l, m ----
+  for (int tb = tile_begin; tb < tile_end; tb += TM_BWD_ROUND) {
+    const int in_round = min(TM_BWD_ROUND, tile_end - tb);
+    // ---- phase 1: one tile per warp (warps 0..3): candidates, P^, P^ (d2 - m), 1/l, m ----
     if (warp < in_round) {
       Point<GEO> col[CPL];
 #pragma unroll
@@ -566,21 +630,24 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
       const int row = (tb + warp) * TM_ROWS + (lane & 15);
       const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row, s);
       const int cnt = tm_candidates<GEO, CPL, NH>(R, col, P.M, lane, period, cand);
-      float psum[NH], pdsum[NH];
-#pragma unroll
-      for (int h = 0; h < NH; ++h) psum[h] = pdsum[h] = 0.f;
-      const int nkb = (cnt + TM_KT - 1) / TM_KT;
-      for (int kb = nkb - 1; kb >= 0; --kb)
-        tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], &T->d2[0][0], psum, pdsum);
+      float psum[NH], pdsum[NH], inv[NH], m[NH];
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
-        const float pd = pdsum[h] + __shfl_xor_sync(FULL, pdsum[h], 16);
+        psum[h] = pdsum[h] = 0.f;
+        inv[h] = R.valid ? 1.f / __ldg(P.rowsum + (int64_t)h * P.N + row) : 0.f;
+      }
+      const int nkb = (cnt + TM_KT - 1) / TM_KT;
+      for (int kb = nkb - 1; kb >= 0; --kb)
+        tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], &T->z[0][0][0], inv, psum, pdsum);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        m[h] = pdsum[h] + __shfl_xor_sync(FULL, pdsum[h], 16);
         if (lane < TM_ROWS) {
-          const float inv = R.valid ? 1.f / __ldg(P.rowsum + (int64_t)h * P.N + row) : 0.f;
-          T->inv_l[h][lane] = inv;
-          T->m[h][lane] = pd * inv;
+          T->inv_l[h][lane] = inv[h];
+          T->m[h][lane] = m[h];
         }
       }
+      if (nkb > 0) tm_block_finish<NH>(cnt, 0, lane, &T->p[0][0][0], &T->z[0][0][0], inv, m);
       for (int k = lane; k < cnt; k += 32) S.touched[cand[k]] = 1;
       if (lane == 0) T->cnt = cnt;
     }
@@ -598,7 +665,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
         const int chunk = ch0 + warp;
         const bool active = chunk < chunks;
         const int xcol = chunk * TM_CHUNK + TM_TPC * g;  // first of this thread's columns of the B*C-wide vector
-        const int b = active ? xcol / P.C : 0;
+        const int b = active ? xcol >> log2c : 0;
         const float* y_chunk = P.y + (size_t)b * P.M * NH * P.C + c0;
         float acc[TM_MT][2][4];
 #pragma unroll
@@ -611,16 +678,10 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
         for (int kb = 0; kb < nkb; ++kb) {
           if (nkb > 1) {
             __syncthreads();
-            if (warp == 0) {
-              const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row0 + (lane & 15), s);
-              float ps[NH], pd[NH];
-#pragma unroll
-              for (int h = 0; h < NH; ++h) ps[h] = pd[h] = 0.f;
-              tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], &T->d2[0][0], ps, pd);
-            }
+            if (warp == 0) tm_rebuild<GEO, NH, true>(P, T, cand, row0, kb, lane, s, period);
             __syncthreads();
           }
-          if (active) tm_mma_block<NH>(acc, T->p, T->inv_l, cand, cnt, kb, y_chunk, P.C, g, t);
+          if (active) tm_mma_block<NH>(acc, T->p, cand, cnt, kb, y_chunk, P.C, g, t);
         }
         // (b) g1 = gelu'(pre) * (W2^T dOut[b, row, :]) in place; parameter-gradient partials
         if (active) {
@@ -671,25 +732,34 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
             }
           }
         }
-        // (c) dY^T += g1^T . P^  and  dZ^T = g1^T . (P^ (d2 - m)) per head and group of 8 candidates
+        // (c) dY^T += g1^T . P^  and  dZ^T = g1^T . (P^ (d2 - m)) per group of 8 candidates and head
         for (int kb = 0; kb < nkb; ++kb) {
           if (nkb > 1) {
             __syncthreads();
-            if (warp == 0) {
-              const TmRow<GEO, NH> R = tm_row<GEO, NH>(P, row0 + (lane & 15), s);
-              float ps[NH], pd[NH];
-#pragma unroll
-              for (int h = 0; h < NH; ++h) ps[h] = pd[h] = 0.f;
-              tm_block<GEO, NH>(P, R, s, period, cand, cnt, kb, lane, &T->p[0][0][0], &T->d2[0][0], ps, pd);
-            }
+            if (warp == 0) tm_rebuild<GEO, NH, true>(P, T, cand, row0, kb, lane, s, period);
             __syncthreads();
           }
           if (!active) continue;
           const int base = kb * TM_KT;
           const int groups8 = (min(cnt - base, TM_KT) + 7) >> 3;
+          for (int ct = 0; ct < groups8; ++ct) {
+            // this thread's two candidates of the group: 8ct + 2t + e  (dy/dz[mt][2*(col&1) + e])
+            bool live[2], bound[2];
+            int yoff[2];             // element offset of Y[b, j, 0, c0] / d_y[b, j, 0, c0]
+            int soff[2][TM_TPC / 4];  // element offsets of the thread's slot cells (head 0)
 #pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            for (int ct = 0; ct < groups8; ++ct) {
+            for (int e = 0; e < 2; ++e) {
+              const int ci = base + ct * 8 + 2 * t + e;
+              live[e] = ci < cnt;
+              const int j = live[e] ? (int)cand[ci] : 0;
+              const int sidx = live[e] ? (int)S.map[j] : -1;
+              bound[e] = sidx >= 0;
+              yoff[e] = (b * P.M + j) * NH * P.C + c0;
+#pragma unroll
+              for (int v4 = 0; v4 < TM_TPC / 4; ++v4) soff[e][v4] = bound[e] ? sidx * NH * W + tm_slot_pos(xcol + 4 * v4, sidx) : 0;
+            }
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
               float dy[TM_MT][4], dz[TM_MT][4];
 #pragma unroll
               for (int mt = 0; mt < TM_MT; ++mt)
@@ -702,8 +772,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int r = 8 * nt + 2 * t + e;
-                  const float pn = T->p[h][r][ct * 8 + g] * T->inv_l[h][r];
-                  const float pz = pn * (T->d2[r][ct * 8 + g] - T->m[h][r]);
+                  const float pn = T->p[h][r][ct * 8 + g], pz = T->z[h][r][ct * 8 + g];
                   const float h0 = tm_round_hi(pn), h1 = tm_round_hi(pz);
                   ph[e] = __float_as_uint(h0), pl[e] = __float_as_uint(pn - h0);
                   zh[e] = __float_as_uint(h1), zl[e] = __float_as_uint(pz - h1);
@@ -722,47 +791,35 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
                   mma_tf32_16x8x8(dz[mt], ah, zh);
                 }
               }
-              // dy/dz[mt][e]: column TPC*g + 2*mt + (e >> 1), candidate 8ct + 2t + (e & 1)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int ci = base + ct * 8 + 2 * t + e;
-                if (ci < cnt) {
-                  const int j = cand[ci];
-                  // scale gradient: -sum Y_h[j, col] dZ[col, j]
-                  const float2* yr = reinterpret_cast<const float2*>(y_chunk + ((size_t)j * NH + h) * P.C);
-                  float dot = 0.f;
+                if (!live[e]) continue;
+                // scale gradient: -sum Y_h[j, col] dZ[col, j]
+                const float2* yr = reinterpret_cast<const float2*>(P.y + yoff[e] + h * P.C);
+                float dot = 0.f;
 #pragma unroll
-                  for (int mt = 0; mt < TM_MT; ++mt) {
-                    const float2 yv = __ldg(yr + mt);
-                    dot = fmaf(yv.x, dz[mt][e], dot);
-                    dot = fmaf(yv.y, dz[mt][2 + e], dot);
-                  }
-                  ds_head[h] += dot;
-                  // value gradient: the thread owns these TPC cells of the slot (or of d_y itself if the column is unbound)
-                  const int sidx = S.map[j];
-                  if (sidx >= 0) {
+                for (int mt = 0; mt < TM_MT; ++mt) {
+                  const float2 yv = __ldg(yr + mt);
+                  dot = fmaf(yv.x, dz[mt][e], dot);
+                  dot = fmaf(yv.y, dz[mt][2 + e], dot);
+                }
+                ds_head[h] += dot;
+                // value gradient: the thread owns these TPC cells of the slot (or adds to d_y itself if the column is unbound)
 #pragma unroll
-                    for (int v4 = 0; v4 < TM_TPC / 4; ++v4) {
-                      // positions stay 16-byte groups: the rotation is a multiple of 4 floats; the second group may wrap
-                      float4* c4 = reinterpret_cast<float4*>(S.slot_acc + ((size_t)sidx * NH + h) * W + tm_slot_pos(xcol + 4 * v4, sidx));
-                      float4 cur = *c4;
-                      cur.x += dy[2 * v4][e];
-                      cur.y += dy[2 * v4][2 + e];
-                      cur.z += dy[2 * v4 + 1][e];
-                      cur.w += dy[2 * v4 + 1][2 + e];
-                      *c4 = cur;
-                    }
+                for (int v4 = 0; v4 < TM_TPC / 4; ++v4) {
+                  const float4 add = make_float4(dy[2 * v4][e], dy[2 * v4][2 + e], dy[2 * v4 + 1][e], dy[2 * v4 + 1][2 + e]);
+                  if (bound[e]) {
+                    float4* c4 = reinterpret_cast<float4*>(S.slot_acc + soff[e][v4] + h * W);
+                    float4 cur = *c4;
+                    cur.x += add.x, cur.y += add.y, cur.z += add.z, cur.w += add.w;
+                    *c4 = cur;
                   } else {
-                    float* dst = P.d_y + (((size_t)b * P.M + j) * NH + h) * P.C + c0;
-#pragma unroll
-                    for (int v4 = 0; v4 < TM_TPC / 4; ++v4)
-                      atomicAdd(reinterpret_cast<float4*>(dst + 4 * v4),
-                                make_float4(dy[2 * v4][e], dy[2 * v4][2 + e], dy[2 * v4 + 1][e], dy[2 * v4 + 1][2 + e]));
+                    atomicAdd(reinterpret_cast<float4*>(P.d_y + yoff[e] + h * P.C + 4 * v4), add);
                   }
                 }
               }
-              __syncwarp();  // the lanes of a quad may reach the same slot cell in the next group of candidates
             }
+            __syncwarp();  // the lanes of a quad may reach the same slot cell in the next group of candidates
           }
         }
       }
@@ -801,7 +858,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
   // b1 and W2: per-thread partials (channel c0 + i) -> CTA sums in shared memory -> one RED per address
   for (int i = 0; i < TM_TPC; ++i) {
     atomicAdd(&S.gpar[c0 + i], S.priv[i * blockDim.x + tid]);
-    for (int o = 0; o < P.O; ++o) atomicAdd(&S.gpar[(1 + o) * P.C + c0 + i], S.priv[((1 + o) * TM_TPC + i) * blockDim.x + tid]);
+    for (int o = 0; o < n_out; ++o) atomicAdd(&S.gpar[(1 + o) * P.C + c0 + i], S.priv[((1 + o) * TM_TPC + i) * blockDim.x + tid]);
   }
   __syncthreads();
   for (int i = tid; i < n_par; i += blockDim.x) atomicAdd(i < P.C ? P.d_b1 + i : P.d_w2 + (i - P.C), S.gpar[i]);

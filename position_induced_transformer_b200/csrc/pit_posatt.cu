@@ -400,7 +400,7 @@ void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c) {
   const int tiles = (p->n_out + pit::TM_ROWS - 1) / pit::TM_ROWS;
   const int target = sm_count() * 2;
   int per_cta = (tiles + target - 1) / target;
-  per_cta = (per_cta + pit::TM_ROUND - 1) / pit::TM_ROUND * pit::TM_ROUND;
+  per_cta = (per_cta + pit::TM_MAX_WARPS - 1) / pit::TM_MAX_WARPS * pit::TM_MAX_WARPS;
   c.rows_per_unit = per_cta;
   c.grid = (tiles + per_cta - 1) / per_cta;
   c.cpl = cpl_of(p->n_in);
@@ -410,7 +410,7 @@ TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
   TallPlan c{};
   if (!tail_mma_eligible(p, out_dim)) return c;
   plan_tail_mma_grid(p, c);
-  c.smem = pit::tm_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim);
+  c.smem = pit::tm_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim, c.threads);
   if (c.smem > (size_t)max_smem_optin() - 1024) return c;
   c.ok = true;
   return c;
