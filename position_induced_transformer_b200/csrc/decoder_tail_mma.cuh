@@ -45,8 +45,9 @@ constexpr int TM_TPC = 2 * TM_MT;     // contiguous columns a thread owns inside
 constexpr int TM_MAX_WARPS = 8;
 constexpr int TM_BWD_ROUND = 4;  // tiles prepared per round in the backward (warps 0..3): keeps shared memory for dY slots
 
+// (not volatile: the scheduler may interleave independent accumulator chains)
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
@@ -267,15 +268,20 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const fl
         bh[nt][0] = __float_as_uint(h0), bh[nt][1] = __float_as_uint(h1);
         bl[nt][0] = __float_as_uint(p0 - h0), bl[nt][1] = __float_as_uint(p1 - h1);
       }
+      // split terms outermost: the dependent MMAs on one accumulator are eight instructions apart
 #pragma unroll
       for (int mt = 0; mt < TM_MT; ++mt) {
-        const uint32_t ah[4] = {__float_as_uint(ya[mt].x), __float_as_uint(ya[mt].y), __float_as_uint(yb[mt].x), __float_as_uint(yb[mt].y)};
         const uint32_t al[4] = {tm_trunc_lo(ya[mt].x), tm_trunc_lo(ya[mt].y), tm_trunc_lo(yb[mt].x), tm_trunc_lo(yb[mt].y)};
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          mma_tf32_16x8x8(acc[mt][nt], al, bh[nt]);
-          mma_tf32_16x8x8(acc[mt][nt], ah, bl[nt]);
-          mma_tf32_16x8x8(acc[mt][nt], ah, bh[nt]);
+        for (int nt = 0; nt < 2; ++nt) mma_tf32_16x8x8(acc[mt][nt], al, bh[nt]);
+      }
+#pragma unroll
+      for (int term = 0; term < 2; ++term) {
+#pragma unroll
+        for (int mt = 0; mt < TM_MT; ++mt) {
+          const uint32_t ah[4] = {__float_as_uint(ya[mt].x), __float_as_uint(ya[mt].y), __float_as_uint(yb[mt].x), __float_as_uint(yb[mt].y)};
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32_16x8x8(acc[mt][nt], ah, term == 0 ? bl[nt] : bh[nt]);
         }
       }
     }
@@ -777,18 +783,23 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
                   ph[e] = __float_as_uint(h0), pl[e] = __float_as_uint(pn - h0);
                   zh[e] = __float_as_uint(h1), zl[e] = __float_as_uint(pz - h1);
                 }
+                // A fragments: the accumulator registers of g1^T, reordered (m = column, k = row); split terms outermost
 #pragma unroll
                 for (int mt = 0; mt < TM_MT; ++mt) {
-                  // A fragments: the accumulator registers of g1^T, reordered (m = column, k = row)
                   const float a0 = acc[mt][nt][0], a1 = acc[mt][nt][2], a2 = acc[mt][nt][1], a3 = acc[mt][nt][3];
-                  const uint32_t ah[4] = {__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3)};
                   const uint32_t al[4] = {tm_trunc_lo(a0), tm_trunc_lo(a1), tm_trunc_lo(a2), tm_trunc_lo(a3)};
                   mma_tf32_16x8x8(dy[mt], al, ph);
-                  mma_tf32_16x8x8(dy[mt], ah, pl);
-                  mma_tf32_16x8x8(dy[mt], ah, ph);
                   mma_tf32_16x8x8(dz[mt], al, zh);
-                  mma_tf32_16x8x8(dz[mt], ah, zl);
-                  mma_tf32_16x8x8(dz[mt], ah, zh);
+                }
+#pragma unroll
+                for (int term = 0; term < 2; ++term) {
+#pragma unroll
+                  for (int mt = 0; mt < TM_MT; ++mt) {
+                    const uint32_t ah[4] = {__float_as_uint(acc[mt][nt][0]), __float_as_uint(acc[mt][nt][2]), __float_as_uint(acc[mt][nt][1]),
+                                            __float_as_uint(acc[mt][nt][3])};
+                    mma_tf32_16x8x8(dy[mt], ah, term == 0 ? pl : ph);
+                    mma_tf32_16x8x8(dz[mt], ah, term == 0 ? zl : zh);
+                  }
                 }
               }
 #pragma unroll
