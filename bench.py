@@ -237,7 +237,7 @@ def run_ours(args, rank, world, local_rank):
     w = workloads.WORKLOADS[args.workload](batch).to(dev)
     model = w.model
     use_graph = not args.no_graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph, fused=True)   # torch's single-kernel Adam
     gen = torch.Generator().manual_seed(1234 + rank)
     n_buf = 4
     host = [w.make_batch(gen, batch) for _ in range(n_buf)]
@@ -255,10 +255,12 @@ def run_ours(args, rank, world, local_rank):
         flat = FlatGradients(model.parameters(), world)
 
         def step(ins, target):
-            flat.zero()
+            flat.release()
             loss = forward_loss(ins, target)
             loss.backward()
-            flat.all_reduce()
+            if world > 1:
+                flat.gather()
+                flat.all_reduce()
             opt.step()
             return loss
 

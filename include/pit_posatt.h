@@ -9,6 +9,7 @@
  *   pit_rowstat             the row sort inside torch.quantile    pit.py:49, 136, 197, 255
  *   pit_posatt_forward      dist2att + convolution (+ concat)     pit.py:46-57, 133-144, 190-200, 247-258, 37-44
  *   pit_posatt_backward     what autograd replays for the above   (no explicit code in the reference)
+ *   pit_head_scale*         the scale map tan(c*(1+sin(lmda)))    pit.py:48, 135, 196, 254
  *
  * Conventions
  *   - all tensors are fp32, contiguous, row-major, resident on the CURRENT CUDA device;
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 1
+#define PIT_ABI_VERSION 2
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -108,6 +109,15 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
                         int64_t ld_out, int64_t col_off, int32_t accumulate_concat,
                         float* d_values, float* d_scale, void* workspace, size_t workspace_bytes,
                         void* stream);
+
+/* Per-head scale map of pit.py:48:  scale[i] = tan(c * (1 + sin(lmda[i]))),  c = fp32(0.25*pi*(1-1e-7)),
+ * each operation rounded to fp32 separately as the reference's chain of torch ops does (sin, add, mul, tan:
+ * four launches there, one here), and its derivative
+ *   d_lmda[i] = d_scale[i] * c * cos(lmda[i]) * (1 + scale[i]^2)
+ * (seven launches of autograd there).  n = number of heads; all pointers device. */
+int pit_head_scale_forward(const float* lmda, float* scale, int32_t n, void* stream);
+int pit_head_scale_backward(const float* lmda, const float* scale, const float* d_scale, float* d_lmda, int32_t n,
+                            void* stream);
 
 /* Fused decoder tail: pit.decoder (pit.py:124-127) = cross position-attention `up` + kaiming_mlp `de`
  * (pit.py:21-26), for shared meshes with M <= 1024, H <= 2, hidden width C a power of two in [32, 512], out_dim <= 4.

@@ -472,6 +472,22 @@ pit::TailParams tail_params(const pit_problem_t* p, const TallPlan& c, const flo
   return P;
 }
 
+// scale map of pit.py:48 and its derivative (libdevice sinf / tanf, no fast-math: same functions torch's kernels call)
+__global__ void head_scale_fwd_kernel(const float* __restrict__ lmda, float* __restrict__ scale, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c = (float)(0.25 * 3.141592653589793 * (1 - 1e-7));
+  scale[i] = tanf(__fmul_rn(c, __fadd_rn(1.0f, sinf(lmda[i]))));
+}
+__global__ void head_scale_bwd_kernel(const float* __restrict__ lmda, const float* __restrict__ scale,
+                                      const float* __restrict__ d_scale, float* __restrict__ d_lmda, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c = (float)(0.25 * 3.141592653589793 * (1 - 1e-7));
+  const float s = scale[i];
+  d_lmda[i] = d_scale[i] * fmaf(s, s, 1.0f) * c * cosf(lmda[i]);
+}
+
 }  // namespace
 
 extern "C" {
@@ -744,6 +760,22 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   return PIT_OK;
 }
 
+
+int pit_head_scale_forward(const float* lmda, float* scale, int32_t n, void* stream) {
+  if (!lmda || !scale || n < 1) return fail(PIT_ERR_ARG, "head scale: bad arguments");
+  head_scale_fwd_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(lmda, scale, n);
+  PIT_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
+int pit_head_scale_backward(const float* lmda, const float* scale, const float* d_scale, float* d_lmda, int32_t n, void* stream) {
+  if (!lmda || !scale || !d_scale || !d_lmda || n < 1) return fail(PIT_ERR_ARG, "head scale: bad arguments");
+  head_scale_bwd_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(lmda, scale, d_scale, d_lmda, n);
+  PIT_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
 
 int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim) {
   if (check_problem(p) != PIT_OK) return 0;

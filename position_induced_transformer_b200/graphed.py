@@ -44,10 +44,12 @@ class GraphedTrainStep:
             self.loss = self._eager()
 
     def _eager(self):
-        self.flat.zero()
+        self.flat.release()                     # grads None, as optimizer.zero_grad() leaves them: no fill, no accumulation adds
         loss = self.forward_loss(self.static_inputs, self.static_target)
         loss.backward()
-        self.flat.all_reduce()
+        if self.flat.world_size > 1:
+            self.flat.gather()                  # one multi-tensor copy into the flat bucket
+            self.flat.all_reduce()
         self.optimizer.step()
         return loss.detach()
 

@@ -319,6 +319,40 @@ def position_attention(mesh_out: torch.Tensor, mesh_in: torch.Tensor, values: to
 
 
 # ----------------------------------------------------------------------------------------------
+# per-head scale map s = tan(c (1 + sin lmda)) (pit.py:48): one launch forward, one backward
+# ----------------------------------------------------------------------------------------------
+class _HeadScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lmda):
+        _require(lmda.is_cuda and lmda.dtype == torch.float32, "head_scale: lmda must be a float32 CUDA tensor")
+        flat = lmda.detach().reshape(-1).contiguous()
+        scale = torch.empty_like(flat)
+        with torch.cuda.device(lmda.device):
+            _cabi.check(_cabi.lib.pit_head_scale_forward(flat.data_ptr(), scale.data_ptr(), flat.numel(), _stream(lmda.device)),
+                        "pit_head_scale_forward")
+        ctx.save_for_backward(flat, scale)
+        ctx.lmda_shape = lmda.shape
+        return scale.view(lmda.shape)
+
+    @staticmethod
+    def backward(ctx, d_scale):
+        flat, scale = ctx.saved_tensors
+        d_scale = d_scale.reshape(-1).contiguous()
+        d_lmda = torch.empty_like(flat)
+        with torch.cuda.device(flat.device):
+            _cabi.check(_cabi.lib.pit_head_scale_backward(flat.data_ptr(), scale.data_ptr(), d_scale.data_ptr(), d_lmda.data_ptr(),
+                                                          flat.numel(), _stream(flat.device)), "pit_head_scale_backward")
+        return d_lmda.view(ctx.lmda_shape)
+
+
+@torch.compiler.disable
+def head_scale_cuda(lmda: torch.Tensor) -> torch.Tensor:
+    """tan(c * (1 + sin(lmda))) with c = fp32(0.25 pi (1 - 1e-7)), rounded operation by operation like the reference's
+    chain of torch ops (checked bit for bit against them in tests/test_posatt_gpu.py)."""
+    return _HeadScale.apply(lmda)
+
+
+# ----------------------------------------------------------------------------------------------
 # fused decoder tail: cross position-attention + two-layer MLP (pit.decoder, pit.py:124-127)
 # ----------------------------------------------------------------------------------------------
 class _DecoderTail(torch.autograd.Function):

@@ -1,6 +1,9 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list into a markdown table.
 
-    python scripts/summarize_launches.py gpurun_out/launches.csv "title" > profiles/<name>.md
+    python scripts/summarize_launches.py gpurun_out/launches.csv "title" [anchor-regex] > profiles/<name>.md
+
+With an anchor regex (a kernel launched exactly once per step, e.g. "tail.*fwd") only the launches between its last
+two occurrences are summarised: exactly one training step of a capture that spans several.
 """
 import collections
 import csv
@@ -8,13 +11,16 @@ import re
 import sys
 
 
-def main(path, title):
+def main(path, title, anchor=None):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if anchor:
+        hits = [i for i, r in enumerate(rows) if re.search(anchor, r["Kernel Name"])]
+        if len(hits) >= 2:
+            rows = rows[hits[-2] + 1:hits[-1] + 1]
     agg, total = collections.OrderedDict(), 0.0
-    for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+    for row in rows:
         name = re.sub(r"\(.*", "", row["Kernel Name"])[:100]
         v = float(row["Metric Value"].replace(",", ""))
         v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(row["Metric Unit"], v)
@@ -32,4 +38,4 @@ def main(path, title):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "ncu launch list")
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "ncu launch list", sys.argv[3] if len(sys.argv) > 3 else None)

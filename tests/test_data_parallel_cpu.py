@@ -71,3 +71,22 @@ def test_grads_stay_views_after_steps():
     p = next(model.parameters())
     assert p.grad.untyped_storage().data_ptr() == flat.buffer.untyped_storage().data_ptr()
     assert float(flat.buffer.abs().sum()) > 0
+
+
+def test_release_gather_equals_accumulate():
+    """release() + backward + gather() packs the same gradients that zero() + backward accumulates into the views."""
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.GELU(), torch.nn.Linear(7, 2))
+    x = torch.randn(11, 5)
+    flat = FlatGradients(model.parameters(), world_size=1)
+    flat.zero()
+    model(x).square().sum().backward()
+    want = flat.buffer.clone()
+    flat.release()
+    assert all(p.grad is None for p in model.parameters())
+    model(x).square().sum().backward()
+    flat.gather()
+    flat.all_reduce()
+    assert torch.equal(flat.buffer, want)
+    for p in model.parameters():
+        assert p.grad.untyped_storage().data_ptr() == flat.buffer.untyped_storage().data_ptr()

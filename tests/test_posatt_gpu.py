@@ -209,3 +209,25 @@ def test_rowstat_cache_hits_and_invalidates(cuda_device):
     assert posatt.rowstat_cache.misses == m0 + 2
     want = po.dense_contract(po.dense_attention(mo.cpu(), mi.cpu(), scale.cpu().reshape(-1, 1, 1), 0.1), vals.cpu())
     assert rel_linf(c.cpu(), want) <= FWD_TOL
+
+
+def test_head_scale_matches_torch_ops_bit_for_bit(cuda_device):
+    """The one-launch scale map equals the reference's chain of torch CUDA ops (pit.py:48) exactly, and so does its derivative
+    up to rounding."""
+    from math import pi
+    from position_induced_transformer_b200.posatt import head_scale_cuda
+    g = torch.Generator().manual_seed(5)
+    lmda = (torch.rand(100000, 1, 1, generator=g) * 8 - 4).to(cuda_device)
+    lmda[:1000] = torch.rand(1000, 1, 1, generator=g).to(cuda_device)      # the initialisation range of pit.py:35
+    a = lmda.clone().requires_grad_(True)
+    b = lmda.clone().requires_grad_(True)
+    want = torch.tan(0.25 * pi * (1 - 1e-7) * (1.0 + torch.sin(a)))
+    got = head_scale_cuda(b)
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
+    up = torch.randn(want.shape, generator=g).to(cuda_device)
+    want.backward(up)
+    got.backward(up)
+    assert b.grad.shape == a.grad.shape
+    err = ((b.grad - a.grad).abs() / a.grad.abs().clamp_min(1e-30)).max()
+    assert float(err) <= 1e-5
