@@ -38,8 +38,8 @@ STEP_DESC = "zero_grad+forward+RelLp loss+backward+grad allreduce(SUM)+Adam"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="darcy421")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = the reference script's batch size)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

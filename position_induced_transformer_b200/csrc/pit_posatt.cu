@@ -255,7 +255,9 @@ WidePlan plan_wide(const pit_problem_t* p, const pit_rowstat_t* st) {
   w.smem = ((size_t)p->n_out * pit::wide_row_words(p->n_head) + 2 * (size_t)width) * sizeof(float);
   if (w.smem + (size_t)p->n_out * p->n_head * 32 * sizeof(float) > 160 * 1024) return w;
   const int64_t warps = ((int64_t)p->n_in + 32 * pit::WIDE_CPL - 1) / (32 * pit::WIDE_CPL);
-  w.grid = (int)((warps + pit::WIDE_WARPS - 1) / pit::WIDE_WARPS);
+  const int64_t groups = (warps + pit::WIDE_WARPS - 1) / pit::WIDE_WARPS;  // 256 columns each
+  const int64_t per_cta = (groups + 2 * sm_count() - 1) / (2 * sm_count());  // grid-stride: equal shares, <= 2 CTAs per SM
+  w.grid = (int)((groups + per_cta - 1) / per_cta);
   w.ok = true;
   return w;
 }
@@ -393,14 +395,15 @@ bool tail_mma_eligible(const pit_problem_t* p, int out_dim) {
   return tail_mma_enabled() && tail_eligible(p, out_dim) && (c == 32 || c == 64) && ((int64_t)p->batch * c) % pit::TM_CHUNK == 0;
 }
 
-// rows_per_unit counts 16-row tiles per CTA; one 64-column chunk per warp, at most 8 warps
-void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c) {
+// rows_per_unit counts 16-row tiles per CTA; one 64-column chunk per warp, at most 8 warps.  Large meshes get whole
+// rounds per CTA; small ones (fewer tiles than CTA slots x round) get one CTA per few tiles instead -- more SMs beat full rounds.
+void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c, int round) {
   const int chunks = p->batch * p->dim / pit::TM_CHUNK;
   c.threads = chunks <= 4 ? 128 : 256;
   const int tiles = (p->n_out + pit::TM_ROWS - 1) / pit::TM_ROWS;
   const int target = sm_count() * 2;
   int per_cta = (tiles + target - 1) / target;
-  per_cta = (per_cta + pit::TM_MAX_WARPS - 1) / pit::TM_MAX_WARPS * pit::TM_MAX_WARPS;
+  if (per_cta >= round) per_cta = (per_cta + round - 1) / round * round;
   c.rows_per_unit = per_cta;
   c.grid = (tiles + per_cta - 1) / per_cta;
   c.cpl = cpl_of(p->n_in);
@@ -409,7 +412,7 @@ void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c) {
 TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
   TallPlan c{};
   if (!tail_mma_eligible(p, out_dim)) return c;
-  plan_tail_mma_grid(p, c);
+  plan_tail_mma_grid(p, c, pit::TM_MAX_WARPS);
   c.smem = pit::tm_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim, c.threads);
   if (c.smem > (size_t)max_smem_optin() - 1024) return c;
   c.ok = true;
@@ -419,7 +422,7 @@ TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
 TallPlan plan_tail_mma_bwd(const pit_problem_t* p, int out_dim) {
   TallPlan c{};
   if (!tail_mma_eligible(p, out_dim)) return c;
-  plan_tail_mma_grid(p, c);
+  plan_tail_mma_grid(p, c, pit::TM_BWD_ROUND);
   const int W = p->batch * p->dim;
   const size_t fixed = pit::tm_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, 0, c.threads);
   const size_t per_slot = (size_t)p->n_head * W * 4 + 2;

@@ -119,8 +119,10 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float period = P.period ? __ldg(P.period) : 0.f;
-  const int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL);
-  if (base >= P.M) return;
+  // A CTA takes several groups of 4 x 64 columns (grid-stride): the row table (and, backward, the upstream-gradient table)
+  // is built once per CTA, not once per 256 columns.
+  const int64_t stride = (int64_t)gridDim.x * WIDE_WARPS * (32 * WIDE_CPL);
+  for (int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL); base < P.M; base += stride) {
   Point<GEO> col[WIDE_CPL];
   int jcol[WIDE_CPL];
 #pragma unroll
@@ -172,19 +174,32 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams
       for (int c = 0; c < WIDE_CPL; ++c) lsum += p[c][h];
       lsum = warp_sum(lsum);
       if (lsum > 0.f) {  // warp-uniform
-        float mine = 0.f;  // lane e ends up with element e of the warp's partial sum
+        // lane e ends up with element e of the warp's partial sum: a reduce-scatter butterfly (31 shuffles) instead of one
+        // full warp reduction per element (5 x WPAD shuffles)
+        float v[32];
 #pragma unroll
-        for (int e = 0; e < WPAD; ++e) {
-          float part = 0.f;
+        for (int e = 0; e < 32; ++e) {
+          v[e] = 0.f;
+          if (e < WPAD) {
 #pragma unroll
-          for (int c = 0; c < WIDE_CPL; ++c) part = fmaf(p[c][h], u[c][e], part);
-          part = warp_sum(part);
-          if (lane == e) mine = part;
+            for (int c = 0; c < WIDE_CPL; ++c) v[e] = fmaf(p[c][h], u[c][e], v[e]);
+          }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const bool upper = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < o; ++i) {
+            const float keep = upper ? v[i + o] : v[i], send = upper ? v[i] : v[i + o];
+            v[i] = keep + __shfl_xor_sync(FULL, send, o);
+          }
+        }
+        const float mine = v[0];
         if (lane < P.width) atomicAdd(P.partial + ((int64_t)r * NH + h) * P.width + lane, mine);
         if (lane == 0) atomicAdd(P.rowsum + (int64_t)h * P.N + r, lsum);
       }
     }
+  }
   }
 }
 
@@ -211,8 +226,10 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WidePar
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float period = P.period ? __ldg(P.period) : 0.f;
-  const int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL);
-  if (base >= P.M) return;
+  // A CTA takes several groups of 4 x 64 columns (grid-stride): the row table (and, backward, the upstream-gradient table)
+  // is built once per CTA, not once per 256 columns.
+  const int64_t stride = (int64_t)gridDim.x * WIDE_WARPS * (32 * WIDE_CPL);
+  for (int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL); base < P.M; base += stride) {
   Point<GEO> col[WIDE_CPL];
   int jcol[WIDE_CPL];
 #pragma unroll
@@ -285,6 +302,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WidePar
         }
       }
     }
+  }
   }
 }
 
