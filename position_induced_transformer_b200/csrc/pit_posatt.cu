@@ -255,8 +255,8 @@ WidePlan plan_wide(const pit_problem_t* p, const pit_rowstat_t* st) {
   w.smem = ((size_t)p->n_out * pit::wide_row_words(p->n_head) + 2 * (size_t)width) * sizeof(float);
   if (w.smem + (size_t)p->n_out * p->n_head * 32 * sizeof(float) > 160 * 1024) return w;
   const int64_t warps = ((int64_t)p->n_in + 32 * pit::WIDE_CPL - 1) / (32 * pit::WIDE_CPL);
-  const int64_t groups = (warps + pit::WIDE_WARPS - 1) / pit::WIDE_WARPS;  // 256 columns each
-  const int64_t per_cta = (groups + 2 * sm_count() - 1) / (2 * sm_count());  // grid-stride: equal shares, <= 2 CTAs per SM
+  const int64_t groups = (warps + pit::WIDE_WARPS - 1) / pit::WIDE_WARPS;  // 512 columns each
+  const int64_t per_cta = (groups + 4 * sm_count() - 1) / (4 * sm_count());  // grid-stride: equal shares, <= 4 CTAs per SM
   w.grid = (int)((groups + per_cta - 1) / per_cta);
   w.ok = true;
   return w;

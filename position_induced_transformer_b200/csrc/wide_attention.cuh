@@ -17,7 +17,7 @@
 
 namespace pit {
 
-constexpr int WIDE_THREADS = 128;
+constexpr int WIDE_THREADS = 256;  // 8 warps share one row table: 512 columns per CTA pass
 constexpr int WIDE_WARPS = WIDE_THREADS / 32;
 constexpr int WIDE_CPL = 2;       // columns per lane: 64 columns per warp (more warps: the row walk is latency bound)
 constexpr int WIDE_MAX_WIDTH = 32;  // B*D scalars per value row
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float period = P.period ? __ldg(P.period) : 0.f;
-  // A CTA takes several groups of 4 x 64 columns (grid-stride): the row table (and, backward, the upstream-gradient table)
+  // A CTA takes one or more groups of 8 x 64 columns (grid-stride): the row table (and, backward, the upstream-gradient table)
   // is built once per CTA, not once per 256 columns.
   const int64_t stride = (int64_t)gridDim.x * WIDE_WARPS * (32 * WIDE_CPL);
   for (int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL); base < P.M; base += stride) {
@@ -211,22 +211,26 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WidePar
   int* val_off = reinterpret_cast<int*>(rowtab + (size_t)P.N * rw);
   float* gtab = reinterpret_cast<float*>(val_off + P.width);  // [N][NH][WPAD] upstream gradient rows
   wide_build_rows<GEO>(P, rowtab, val_off, nullptr);
-  for (int idx = threadIdx.x; idx < P.N * NH * WPAD; idx += WIDE_THREADS) {
-    const int e = idx % WPAD;
-    const int h = (idx / WPAD) % NH;
-    const int r = idx / (WPAD * NH);
-    float g = 0.f;
-    if (e < P.width) {
-      const int b = e / P.D, d = e - b * P.D;
-      g = __ldg(P.d_out + ((int64_t)b * P.N + r) * P.ld_out + P.col_off + (int64_t)h * P.D + d);
+  // one (row, head) pair per thread and pass: WPAD independent loads in flight, sample/channel counters instead of divisions
+  for (int rh = threadIdx.x; rh < P.N * NH; rh += WIDE_THREADS) {
+    const int r = rh / NH, h = rh - r * NH;
+    const float* src = P.d_out + (int64_t)r * P.ld_out + P.col_off + (int64_t)h * P.D;
+    float* g = gtab + (size_t)rh * WPAD;
+    int b = 0, d = 0;
+#pragma unroll
+    for (int e = 0; e < WPAD; ++e) {
+      g[e] = e < P.width ? __ldg(src + (int64_t)b * P.N * P.ld_out + d) : 0.f;
+      if (++d == P.D) {
+        d = 0;
+        ++b;
+      }
     }
-    gtab[idx] = g;
   }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float period = P.period ? __ldg(P.period) : 0.f;
-  // A CTA takes several groups of 4 x 64 columns (grid-stride): the row table (and, backward, the upstream-gradient table)
+  // A CTA takes one or more groups of 8 x 64 columns (grid-stride): the row table (and, backward, the upstream-gradient table)
   // is built once per CTA, not once per 256 columns.
   const int64_t stride = (int64_t)gridDim.x * WIDE_WARPS * (32 * WIDE_CPL);
   for (int64_t base = ((int64_t)blockIdx.x * WIDE_WARPS + warp) * (32 * WIDE_CPL); base < P.M; base += stride) {
