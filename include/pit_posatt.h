@@ -10,6 +10,7 @@
  *   pit_posatt_forward      dist2att + convolution (+ concat)     pit.py:46-57, 133-144, 190-200, 247-258, 37-44
  *   pit_posatt_backward     what autograd replays for the above   (no explicit code in the reference)
  *   pit_head_scale*         the scale map tan(c*(1+sin(lmda)))    pit.py:48, 135, 196, 254
+ *   pit_bias_act*           bias + GELU epilogues of the MLPs     pit.py:21-26, 111, 121
  *
  * Conventions
  *   - all tensors are fp32, contiguous, row-major, resident on the CURRENT CUDA device;
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 2
+#define PIT_ABI_VERSION 3
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -118,6 +119,18 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
 int pit_head_scale_forward(const float* lmda, float* scale, int32_t n, void* stream);
 int pit_head_scale_backward(const float* lmda, const float* scale, const float* d_scale, float* d_lmda, int32_t n,
                             void* stream);
+
+/* Epilogue of the Linear layers of kaiming_mlp (pit.py:21-26) and of the GELUs around them (pit.py:111, 121):
+ *   out[r,c] = act(z[r,c] + bias[c]),   act = exact (erf) GELU if apply_gelu else identity,
+ * one coalesced 128-bit pass, and its backward in one pass as well:
+ *   d_z[r,c] = d_out[r,c] * act'(z[r,c] + bias[c]),   d_bias[c] = sum_r d_z[r,c]   (overwritten)
+ * -- what autograd does with a GELU-backward kernel plus a separate column reduction.  z is the bias-free GEMM output
+ * [rows, cols]; cols must be a multiple of 4 that divides 1024 (every hidden width of the reference). */
+int pit_bias_act_supported(int64_t rows, int32_t cols);
+int pit_bias_act_forward(const float* z, const float* bias, float* out, int64_t rows, int32_t cols, int32_t apply_gelu,
+                         void* stream);
+int pit_bias_act_backward(const float* z, const float* bias, const float* d_out, float* d_z, float* d_bias, int64_t rows,
+                          int32_t cols, int32_t apply_gelu, void* stream);
 
 /* Fused decoder tail: pit.decoder (pit.py:124-127) = cross position-attention `up` + kaiming_mlp `de`
  * (pit.py:21-26), for shared meshes with M <= 1024, H <= 2, hidden width C a power of two in [32, 512], out_dim <= 4.

@@ -13,13 +13,14 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
     "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward",
     "pit_decoder_tail_supported", "pit_decoder_tail_forward", "pit_decoder_tail_backward",
     "pit_head_scale_forward", "pit_head_scale_backward",
+    "pit_bias_act_supported", "pit_bias_act_forward", "pit_bias_act_backward",
 )
 
 
@@ -58,6 +59,9 @@ def _load() -> C.CDLL:
                                               f32p, f32p, f32p, i32, f32p, f32p, f32p, f32p, f32p, f32p, f32p, p]
     lib.pit_head_scale_forward.argtypes = [f32p, f32p, i32, p]
     lib.pit_head_scale_backward.argtypes = [f32p, f32p, f32p, f32p, i32, p]
+    lib.pit_bias_act_supported.argtypes = [i64, i32]
+    lib.pit_bias_act_forward.argtypes = [f32p, f32p, f32p, i64, i32, i32, p]
+    lib.pit_bias_act_backward.argtypes = [f32p, f32p, f32p, f32p, f32p, i64, i32, i32, p]
     if lib.pit_abi_version() != ABI_VERSION:
         raise ImportError(f"libpit_posatt.so ABI {lib.pit_abi_version()} != expected {ABI_VERSION}; rebuild it")
     return lib

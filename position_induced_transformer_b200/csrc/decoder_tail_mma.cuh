@@ -3,7 +3,7 @@
 // Same contract as decoder_tail.cuh (pit.decoder, pit.py:124-127: cross position-attention `up` + `de` MLP), but
 // the contraction of a row's 6..40 kept weights with the B*C-wide latent rows is no longer a per-row gather on the
 // CUDA cores.  Rows are taken in tiles of 16 consecutive points.  On a spatially coherent mesh the union of the
-// columns kept by ANY row of a tile is barely larger than one row's kept set (12..16 columns at Darcy-421), so
+// columns kept by ANY row of a tile is barely larger than one row's kept set (7.1 -> 8.9 columns at Darcy-421), so
 //
 //     pre^T [(b,c) x 16 rows] = Y^T [(b,c) x candidates] . P^T [candidates x 16 rows]        (per head, summed)
 //

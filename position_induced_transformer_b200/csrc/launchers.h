@@ -8,6 +8,7 @@
 #include "decoder_tail_mma.cuh"
 #include "dense_attention.cuh"
 #include "local_attention.cuh"
+#include "mlp_epilogue.cuh"
 #include "rowstat.cuh"
 #include "tall_attention.cuh"
 #include "wide_attention.cuh"
@@ -48,6 +49,8 @@ cudaError_t tail_mma_backward(int geo, const TallPlan& plan, const TailParams& P
 int wide_pad(int width);
 cudaError_t wide_forward(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
 cudaError_t wide_dscale(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
+// tu_mlp_epilogue.cu
+cudaError_t bias_act(bool backward, const EpiParams& P, int grid, cudaStream_t st);
 // tu_dense.cu  (mode: DENSE_FWD / DENSE_DSCALE / DENSE_DVALUES; nv: 64, 128 or 256 value columns per tile)
 cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cudaStream_t st);
 

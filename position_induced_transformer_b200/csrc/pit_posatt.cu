@@ -780,6 +780,43 @@ int pit_head_scale_backward(const float* lmda, const float* scale, const float* 
   return PIT_OK;
 }
 
+int pit_bias_act_supported(int64_t rows, int32_t cols) {
+  return rows >= 1 && cols >= 4 && cols % 4 == 0 && pit::EPI_THREADS % (cols / 4) == 0 ? 1 : 0;
+}
+
+namespace {
+int bias_act_grid(int64_t rows, int cols4) {
+  const int64_t blocks = (rows * cols4 + pit::EPI_THREADS - 1) / pit::EPI_THREADS;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  return (int)(blocks < cap ? blocks : cap);
+}
+}  // namespace
+
+int pit_bias_act_forward(const float* z, const float* bias, float* out, int64_t rows, int32_t cols, int32_t apply_gelu, void* stream) {
+  if (!z || !bias || !out || !pit_bias_act_supported(rows, cols)) return fail(PIT_ERR_ARG, "bias_act: bad arguments (cols must be a multiple of 4 dividing 1024)");
+  if (!aligned16(z) || !aligned16(bias) || !aligned16(out)) return fail(PIT_ERR_ARG, "bias_act: pointers must be 16-byte aligned");
+  pit::EpiParams P{};
+  P.z = z, P.bias = bias, P.out = out, P.rows = rows, P.cols4 = cols / 4, P.gelu = apply_gelu;
+  PIT_CUDA(launch::bias_act(false, P, bias_act_grid(rows, P.cols4), static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
+int pit_bias_act_backward(const float* z, const float* bias, const float* d_out, float* d_z, float* d_bias, int64_t rows,
+                          int32_t cols, int32_t apply_gelu, void* stream) {
+  if (!z || !bias || !d_out || !d_z || !d_bias || !pit_bias_act_supported(rows, cols))
+    return fail(PIT_ERR_ARG, "bias_act: bad arguments (cols must be a multiple of 4 dividing 1024)");
+  if (!aligned16(z) || !aligned16(bias) || !aligned16(d_out) || !aligned16(d_z) || !aligned16(d_bias))
+    return fail(PIT_ERR_ARG, "bias_act: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pit::EpiParams P{};
+  P.z = z, P.bias = bias, P.d_out = d_out, P.out = d_z, P.d_bias = d_bias, P.rows = rows, P.cols4 = cols / 4, P.gelu = apply_gelu;
+  PIT_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)cols * sizeof(float), st));
+  PIT_CUDA(launch::bias_act(true, P, bias_act_grid(rows, P.cols4), st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
 int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim) {
   if (check_problem(p) != PIT_OK) return 0;
   if (!tail_eligible(p, out_dim)) return 0;

@@ -353,6 +353,52 @@ def head_scale_cuda(lmda: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# bias + GELU epilogue of the MLP Linears (pit.py:21-26, 111, 121): one pass forward, one backward (with the bias gradient)
+# ----------------------------------------------------------------------------------------------
+class _BiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, bias, apply_gelu):
+        z = z.contiguous()
+        bias = bias.contiguous()
+        cols = z.shape[-1]
+        rows = z.numel() // cols
+        out = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            _cabi.check(_cabi.lib.pit_bias_act_forward(z.data_ptr(), bias.data_ptr(), out.data_ptr(), rows, cols, int(apply_gelu),
+                                                       _stream(z.device)), "pit_bias_act_forward")
+        ctx.save_for_backward(z, bias)
+        ctx.apply_gelu = bool(apply_gelu)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        z, bias = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        cols = z.shape[-1]
+        rows = z.numel() // cols
+        d_z = torch.empty_like(z)
+        d_bias = torch.empty_like(bias)
+        with torch.cuda.device(z.device):
+            _cabi.check(_cabi.lib.pit_bias_act_backward(z.data_ptr(), bias.data_ptr(), d_out.data_ptr(), d_z.data_ptr(),
+                                                        d_bias.data_ptr(), rows, cols, int(ctx.apply_gelu), _stream(z.device)),
+                        "pit_bias_act_backward")
+        return d_z, d_bias, None
+
+
+@torch.compiler.disable
+def bias_act_supported(z: torch.Tensor, bias: torch.Tensor) -> bool:
+    """True when the fused epilogue covers this activation: float32 CUDA tensors, width a multiple of 4 dividing 1024."""
+    return (z.is_cuda and z.dtype == torch.float32 and bias.dtype == torch.float32 and bias.device == z.device and z.numel() > 0
+            and bool(_cabi.lib.pit_bias_act_supported(z.numel() // z.shape[-1], z.shape[-1])))
+
+
+@torch.compiler.disable
+def bias_act(z: torch.Tensor, bias: torch.Tensor, apply_gelu: bool) -> torch.Tensor:
+    """act(z + bias) with act = exact GELU or identity; backward returns d_z and d_bias = column sums in the same pass."""
+    return _BiasAct.apply(z, bias, bool(apply_gelu))
+
+
+# ----------------------------------------------------------------------------------------------
 # fused decoder tail: cross position-attention + two-layer MLP (pit.decoder, pit.py:124-127)
 # ----------------------------------------------------------------------------------------------
 class _DecoderTail(torch.autograd.Function):
