@@ -68,6 +68,7 @@ struct DenseParams {
   // DVALUES
   float* d_values;  // [B,M,D]
   int add_concat;
+  int split_heads;  // DVALUES: one CTA per head (grid.z = H x samples), partial sums meet in d_values (zero-initialised) by RED
 };
 
 // ---------------------------------------------------------------------------------------
@@ -237,7 +238,9 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
   const int z = blockIdx.z;
   const int h_fixed = z % P.H;                       // FWD/DSCALE: the head of this CTA
   const int bm = P.mesh_batched ? z / P.H : 0;       // sample (per-sample meshes)
-  const int bm_dv = P.mesh_batched ? z : 0;          // DVALUES: grid.z = samples only
+  const int dv_heads = (MODE == DENSE_DVALUES && P.split_heads) ? P.H : 1;
+  const int h_dv = z % dv_heads;                     // DVALUES with split heads: the head of this CTA
+  const int bm_dv = P.mesh_batched ? z / dv_heads : 0;  // DVALUES: grid.z = samples (x heads when split)
   const int own0 = blockIdx.x * DENSE_ROWS;
   const int n0 = blockIdx.y * NV;
   const float period = P.period ? __ldg(P.period) : 0.f;
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  const int heads_in_k = (MODE == DENSE_DVALUES) ? P.H : 1;
+  const int heads_in_k = (MODE == DENSE_DVALUES && !P.split_heads) ? P.H : 1;
   const int kb_per_head = (P.n_red + DENSE_KB - 1) / DENSE_KB;
   const int n_kb = kb_per_head * heads_in_k;
 
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     // The reduced point of the NEXT K block is fetched while the current block is computed, so the global-load
     // latency (the longest dependency of a K block at small problem sizes) is off the critical path.
     auto fetch = [&](int kb) -> float4 {
-      const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : h_fixed;
+      const int h = (MODE == DENSE_DVALUES) ? h_dv + kb / kb_per_head : h_fixed;
       const int k = (kb % kb_per_head) * DENSE_KB + lane;
       const bool ok = kb < n_kb && k < P.n_red;
       const Point<GEO> q = load_point<GEO>(mesh_red, ok ? k : 0, P.sd);
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     for (int kb = 0; kb < n_kb; ++kb) {
       const int s = kb % DENSE_STAGES;
       const uint32_t use = kb / DENSE_STAGES;
-      const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : h_fixed;
+      const int h = (MODE == DENSE_DVALUES) ? h_dv + kb / kb_per_head : h_fixed;
       const float sc2 = __ldg(P.scale + h) * LOG2E;
       // the 32 reduced points of this block (per-warp copy: no block-level sync needed): (x, y, shift*sc2, post)
       __syncwarp();
@@ -403,14 +406,18 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
               const int b = P.mesh_batched ? sample : n / P.D;
               const int d = P.mesh_batched ? n : n - b * P.D;
               float4 acc = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-              if (P.add_concat) {
+              if (P.add_concat && h_dv == 0) {
                 const float4 g = __ldg(reinterpret_cast<const float4*>(P.d_out + ((int64_t)b * P.N + own) * P.ld_out + d));
                 acc.x += g.x;
                 acc.y += g.y;
                 acc.z += g.z;
                 acc.w += g.w;
               }
-              *reinterpret_cast<float4*>(P.d_values + ((int64_t)b * P.M + own) * P.D + d) = acc;
+              float4* dst = reinterpret_cast<float4*>(P.d_values + ((int64_t)b * P.M + own) * P.D + d);
+              if (P.split_heads)
+                atomicAdd(dst, acc);  // H partial sums onto zeros: the result does not depend on their order for H = 2
+              else
+                *dst = acc;
             }
           }
         }
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     for (int kb = 0; kb < n_kb; ++kb) {
       const int s = kb % DENSE_STAGES;
       const uint32_t use = kb / DENSE_STAGES;
-      const int h = (MODE == DENSE_DVALUES) ? kb / kb_per_head : 0;
+      const int h = (MODE == DENSE_DVALUES) ? h_dv + kb / kb_per_head : 0;
       const int k0 = (kb % kb_per_head) * DENSE_KB;
       // issue the global loads before waiting for the stage to drain
       float4 v[PASSES];

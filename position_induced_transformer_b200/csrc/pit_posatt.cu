@@ -323,9 +323,19 @@ pit::DenseParams dense_params(const pit_problem_t* p, const float* mesh_out, con
   return P;
 }
 
+// Value gradient of a small stage: its K loop runs over the rows of every head; when the grid is far from filling the chip the
+// heads go to separate CTAs instead (half the serial K blocks each) and meet in d_values with REDs.
+bool dense_split_heads(const pit_problem_t* p) {
+  if (p->n_head < 2) return false;
+  const int64_t width = p->mesh_batched ? p->dim : (int64_t)p->batch * p->dim;
+  const int64_t ctas = (int64_t)((p->n_in + pit::DENSE_ROWS - 1) / pit::DENSE_ROWS) * ((width + 63) / 64) * (p->mesh_batched ? p->batch : 1);
+  return ctas * p->n_head <= sm_count();
+}
+
 cudaError_t dense_launch(int mode, int geo, const pit_problem_t* p, const pit::DenseParams& P, cudaStream_t st) {
   const int row_tiles = (P.n_own + pit::DENSE_ROWS - 1) / pit::DENSE_ROWS;
-  const int z = mode == pit::DENSE_DVALUES ? (p->mesh_batched ? p->batch : 1) : p->n_head * (p->mesh_batched ? p->batch : 1);
+  const int z = mode == pit::DENSE_DVALUES ? (p->mesh_batched ? p->batch : 1) * (P.split_heads ? p->n_head : 1)
+                                           : p->n_head * (p->mesh_batched ? p->batch : 1);
   // widest tile that still gives the GPU enough CTAs; the scale-gradient mode holds two accumulators (max 128 columns each)
   int nv = mode == pit::DENSE_DSCALE ? 128 : 256;
   while (nv > 64 && ((int64_t)row_tiles * z * ((P.width + nv - 1) / nv) < sm_count() || nv / 2 >= P.width)) nv /= 2;
@@ -683,6 +693,8 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
       Dn.col_off = col_off;
       Dn.d_values = d_values;
       Dn.add_concat = accumulate_concat;
+      Dn.split_heads = dense_split_heads(p) ? 1 : 0;
+      if (Dn.split_heads) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
       PIT_CUDA(dense_launch(pit::DENSE_DVALUES, geo, p, Dn, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
       values_done = true;
