@@ -219,8 +219,9 @@ struct DenseSmem {
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
+// The body takes its block coordinates as an argument so that two modes can share one launch (dense_bwd_pair_kernel).
 template <int GEO, int MODE, int NV>
-__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const DenseParams P) {
+__device__ __forceinline__ void dense_attention_body(const DenseParams& P, const dim3 bid) {
   using L = DenseSmem<MODE, NV>;
   constexpr int ACC_COLS = (MODE == DENSE_DSCALE) ? 2 * NV : NV;
   constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
@@ -235,14 +236,14 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
   float4* red_pts = reinterpret_cast<float4*>(tiles_ptr + DENSE_STAGES * L::STAGE_BYTES);  // [4 warps][32] (x, y, vmin*, post)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int z = blockIdx.z;
+  const int z = bid.z;
   const int h_fixed = z % P.H;                       // FWD/DSCALE: the head of this CTA
   const int bm = P.mesh_batched ? z / P.H : 0;       // sample (per-sample meshes)
   const int dv_heads = (MODE == DENSE_DVALUES && P.split_heads) ? P.H : 1;
   const int h_dv = z % dv_heads;                     // DVALUES with split heads: the head of this CTA
   const int bm_dv = P.mesh_batched ? z / dv_heads : 0;  // DVALUES: grid.z = samples (x heads when split)
-  const int own0 = blockIdx.x * DENSE_ROWS;
-  const int n0 = blockIdx.y * NV;
+  const int own0 = bid.x * DENSE_ROWS;
+  const int n0 = bid.y * NV;
   const float period = P.period ? __ldg(P.period) : 0.f;
   const int sample = (MODE == DENSE_DVALUES) ? bm_dv : bm;
 
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     if (MODE == DENSE_FWD) {
       const float inv_l = 1.f / lsum;
-      if (own_ok && blockIdx.y == 0) P.rowsum_out[((int64_t)sample * P.H + h_fixed) * P.N + own] = lsum;
+      if (own_ok && bid.y == 0) P.rowsum_out[((int64_t)sample * P.H + h_fixed) * P.N + own] = lsum;
       for (int c0 = 0; c0 < NV; c0 += 32) {
         float v[32];
         tmem_ld32(lane_addr + c0, v);  // warp-collective: every lane takes part
@@ -508,5 +509,32 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
+
+template <int GEO, int MODE, int NV>
+__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_attention_kernel(const DenseParams P) {
+  dense_attention_body<GEO, MODE, NV>(P, blockIdx);
+}
+
+// Backward of a small global stage in ONE launch: the scale-gradient CTAs and the value-gradient CTAs are independent
+// (both only read dO), and each set alone covers a fraction of the chip -- side by side they overlap instead of queueing.
+// Blocks [0, n_scale) run the DSCALE body on grid gs, the rest the DVALUES body on grid gv (both linearised x-fastest).
+template <int GEO, int NV>
+__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_bwd_pair_kernel(const DenseParams Ps, const DenseParams Pv, const int n_scale,
+                                                                        const dim3 gs, const dim3 gv) {
+  const bool scale_part = (int)blockIdx.x < n_scale;  // CTA-uniform
+  const dim3 g = scale_part ? gs : gv;
+  const unsigned b = scale_part ? blockIdx.x : blockIdx.x - n_scale;
+  const dim3 bid(b % g.x, (b / g.x) % g.y, b / (g.x * g.y));
+  if (scale_part)
+    dense_attention_body<GEO, DENSE_DSCALE, NV>(Ps, bid);
+  else
+    dense_attention_body<GEO, DENSE_DVALUES, NV>(Pv, bid);
+}
+
+template <int NV>
+struct DensePairSmem {
+  static constexpr int TOTAL = DenseSmem<DENSE_DSCALE, NV>::TOTAL > DenseSmem<DENSE_DVALUES, NV>::TOTAL ? DenseSmem<DENSE_DSCALE, NV>::TOTAL
+                                                                                                       : DenseSmem<DENSE_DVALUES, NV>::TOTAL;
+};
 
 }  // namespace pit

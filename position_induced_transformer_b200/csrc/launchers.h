@@ -53,6 +53,8 @@ cudaError_t wide_dscale(int geo, const WidePlan& w, const WideParams& P, cudaStr
 cudaError_t bias_act(bool backward, const EpiParams& P, int grid, cudaStream_t st);
 // tu_dense.cu  (mode: DENSE_FWD / DENSE_DSCALE / DENSE_DVALUES; nv: 64, 128 or 256 value columns per tile)
 cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cudaStream_t st);
+// both gradient modes of a small stage (64-column tiles) in one launch
+cudaError_t dense_bwd_pair(int geo, const DenseParams& Ps, dim3 gs, const DenseParams& Pv, dim3 gv, cudaStream_t st);
 
 }  // namespace launch
 }  // namespace pit

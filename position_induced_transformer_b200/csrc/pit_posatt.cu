@@ -332,14 +332,20 @@ bool dense_split_heads(const pit_problem_t* p) {
   return ctas * p->n_head <= sm_count();
 }
 
-cudaError_t dense_launch(int mode, int geo, const pit_problem_t* p, const pit::DenseParams& P, cudaStream_t st) {
+dim3 dense_grid(int mode, const pit_problem_t* p, const pit::DenseParams& P, int* nv_out) {
   const int row_tiles = (P.n_own + pit::DENSE_ROWS - 1) / pit::DENSE_ROWS;
   const int z = mode == pit::DENSE_DVALUES ? (p->mesh_batched ? p->batch : 1) * (P.split_heads ? p->n_head : 1)
                                            : p->n_head * (p->mesh_batched ? p->batch : 1);
   // widest tile that still gives the GPU enough CTAs; the scale-gradient mode holds two accumulators (max 128 columns each)
   int nv = mode == pit::DENSE_DSCALE ? 128 : 256;
   while (nv > 64 && ((int64_t)row_tiles * z * ((P.width + nv - 1) / nv) < sm_count() || nv / 2 >= P.width)) nv /= 2;
-  const dim3 grid(row_tiles, (P.width + nv - 1) / nv, z);
+  *nv_out = nv;
+  return dim3(row_tiles, (P.width + nv - 1) / nv, z);
+}
+
+cudaError_t dense_launch(int mode, int geo, const pit_problem_t* p, const pit::DenseParams& P, cudaStream_t st) {
+  int nv = 0;
+  const dim3 grid = dense_grid(mode, p, P, &nv);
   return launch::dense(mode, geo, nv, grid, P, st);
 }
 
@@ -665,40 +671,54 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   // column-owner kernel below (every column is touched by every row, slots would not help).
   bool values_done = d_values == nullptr, scale_done = d_scale == nullptr;
   if (dense_eligible(p, stat)) {
+    pit::DenseParams Ds{}, Dv{};
     if (d_scale) {
-      pit::DenseParams Dn = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_DSCALE);
-      Dn.rowsum = rowsum;
-      Dn.b_src = values;
-      Dn.b_kstride = p->dim;
-      Dn.b_bstride = (int64_t)p->n_in * p->dim;
-      Dn.d_out = d_out;
-      Dn.ld_out = ld_out;
-      Dn.col_off = col_off;
-      Dn.d_scale = d_scale;
+      Ds = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_DSCALE);
+      Ds.rowsum = rowsum;
+      Ds.b_src = values;
+      Ds.b_kstride = p->dim;
+      Ds.b_bstride = (int64_t)p->n_in * p->dim;
+      Ds.d_out = d_out;
+      Ds.ld_out = ld_out;
+      Ds.col_off = col_off;
+      Ds.d_scale = d_scale;
       PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
-      PIT_CUDA(dense_launch(pit::DENSE_DSCALE, geo, p, Dn, st));
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      scale_done = true;
     }
     if (d_values) {
-      pit::DenseParams Dn = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_DVALUES);
-      Dn.rowsum = rowsum;
-      Dn.b_src = d_out;
-      Dn.b_kstride = ld_out;
-      Dn.b_bstride = (int64_t)p->n_out * ld_out;
-      Dn.b_hstride = p->dim;
-      Dn.b_off = col_off;
-      Dn.d_out = d_out;
-      Dn.ld_out = ld_out;
-      Dn.col_off = col_off;
-      Dn.d_values = d_values;
-      Dn.add_concat = accumulate_concat;
-      Dn.split_heads = dense_split_heads(p) ? 1 : 0;
-      if (Dn.split_heads) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
-      PIT_CUDA(dense_launch(pit::DENSE_DVALUES, geo, p, Dn, st));
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      values_done = true;
+      Dv = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_DVALUES);
+      Dv.rowsum = rowsum;
+      Dv.b_src = d_out;
+      Dv.b_kstride = ld_out;
+      Dv.b_bstride = (int64_t)p->n_out * ld_out;
+      Dv.b_hstride = p->dim;
+      Dv.b_off = col_off;
+      Dv.d_out = d_out;
+      Dv.ld_out = ld_out;
+      Dv.col_off = col_off;
+      Dv.d_values = d_values;
+      Dv.add_concat = accumulate_concat;
+      Dv.split_heads = dense_split_heads(p) ? 1 : 0;
+      if (Dv.split_heads) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
     }
+    int nv_s = 0, nv_v = 0;
+    const dim3 gs = d_scale ? dense_grid(pit::DENSE_DSCALE, p, Ds, &nv_s) : dim3(0, 0, 0);
+    const dim3 gv = d_values ? dense_grid(pit::DENSE_DVALUES, p, Dv, &nv_v) : dim3(0, 0, 0);
+    // small stage: neither grid fills the chip -> both gradient modes side by side in one launch
+    if (d_scale && d_values && nv_s == 64 && nv_v == 64 &&
+        (int64_t)gs.x * gs.y * gs.z + (int64_t)gv.x * gv.y * gv.z <= sm_count()) {
+      PIT_CUDA(launch::dense_bwd_pair(geo, Ds, gs, Dv, gv, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+      if (d_scale) {
+        PIT_CUDA(launch::dense(pit::DENSE_DSCALE, geo, nv_s, gs, Ds, st));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+      }
+      if (d_values) {
+        PIT_CUDA(launch::dense(pit::DENSE_DVALUES, geo, nv_v, gv, Dv, st));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+      }
+    }
+    scale_done = values_done = true;
   }
   if (!(values_done && scale_done)) {
     const bool fuse_values = d_values && stat->masked && !accumulate_concat;

@@ -28,5 +28,18 @@ cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cu
   });
 }
 
+cudaError_t dense_bwd_pair(int geo, const DenseParams& Ps, dim3 gs, const DenseParams& Pv, dim3 gv, cudaStream_t st) {
+  return with_geo_only(geo, [&](auto g) -> cudaError_t {
+    constexpr int G = decltype(g)::value;
+    auto kernel = dense_bwd_pair_kernel<G, 64>;
+    constexpr size_t smem = DensePairSmem<64>::TOTAL;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int n_scale = gs.x * gs.y * gs.z, n_values = gv.x * gv.y * gv.z;
+    kernel<<<n_scale + n_values, DENSE_THREADS, smem, st>>>(Ps, Pv, n_scale, gs, gv);
+    return cudaGetLastError();
+  });
+}
+
 }  // namespace launch
 }  // namespace pit
