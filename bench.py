@@ -305,28 +305,39 @@ def run_ours(args, rank, world, local_rank):
     kernels = timer.summary()
 
     # ---- end to end: host inputs, H2D every step, loss read back every step ----
-    # The H2D copy of batch i+1 runs on a copy stream while step i computes (double-buffered staging tensors);
-    # every step still waits for its own inputs and reads its own loss back, all inside the timed region.
+    # The H2D copy of batch i+1 runs on a copy stream while step i computes: it lands in one of two staging tensors, which
+    # step i+1 copies into the graph's static inputs as its first action (the static inputs are read by forward AND
+    # backward, so they cannot be overwritten mid-step).  A staging slot is free again as soon as that device-to-device copy
+    # has run -- not when the whole step has finished.  Every step still waits for its own inputs and reads its own loss back,
+    # all inside the timed region.
     copy_stream = torch.cuda.Stream()
     stage = [(tuple(torch.empty_like(x, device=dev) for x in host[0][0]), torch.empty_like(host[0][1], device=dev)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(i):
         ins, tgt = host[i % n_buf]
         slot = i % 2
         with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])                 # the step that last read this slot has taken its copy
             for dst, src in zip(stage[slot][0], ins):
                 dst.copy_(src, non_blocking=True)
             stage[slot][1].copy_(tgt, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def e2e_loop(n):
+        main = torch.cuda.current_stream()
         prefetch(0)
         for i in range(n):
             slot = i % 2
-            torch.cuda.current_stream().wait_event(ready[slot])
-            loss = step(stage[slot][0], stage[slot][1])
-            copy_stream.wait_stream(torch.cuda.current_stream())   # the other staging slot is free once step i-1 consumed it
+            main.wait_event(ready[slot])
+            if use_graph:
+                step.load(stage[slot][0], stage[slot][1])
+                consumed[slot].record(main)
+                loss = step.replay()
+            else:
+                loss = step(stage[slot][0], stage[slot][1])         # eager: the staging tensors are the step's inputs until it ends
+                consumed[slot].record(main)
             if i + 1 < n:
                 prefetch(i + 1)
             float(loss)                                            # D2H read of the step's result

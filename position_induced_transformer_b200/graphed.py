@@ -53,9 +53,16 @@ class GraphedTrainStep:
         self.optimizer.step()
         return loss.detach()
 
-    def __call__(self, inputs: Sequence[torch.Tensor], target: torch.Tensor) -> torch.Tensor:
+    def load(self, inputs: Sequence[torch.Tensor], target: torch.Tensor) -> None:
+        """Copy a batch into the graph's static input buffers (the source may be reused as soon as this copy has run)."""
         for dst, src in zip(self.static_inputs, inputs):
             dst.copy_(src, non_blocking=True)
         self.static_target.copy_(target, non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
         self.graph.replay()
         return self.loss
+
+    def __call__(self, inputs: Sequence[torch.Tensor], target: torch.Tensor) -> torch.Tensor:
+        self.load(inputs, target)
+        return self.replay()

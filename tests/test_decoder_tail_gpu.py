@@ -39,6 +39,9 @@ def _case(variant, sd, N, M, B, D, H, Cw, O, q, seed):
     ("periodic2d", 2, 1024, 64, 2, 32, 2, 256, 2, 0.1),  # wide hidden layer: one sample spans two register groups
     ("euclid", 2, 300, 100, 3, 16, 2, 128, 4, 1.0),      # unmasked
     ("euclid", 2, 97, 40, 1, 8, 1, 512, 1, 0.2),
+    ("euclid", 2, 600, 700, 2, 16, 2, 64, 1, 0.01),      # tensor-core tail with 32 columns per lane (M > 256)
+    ("periodic2d", 2, 1024, 64, 2, 32, 2, 64, 2, 0.1),   # tensor-core tail, periodic distance, out_dim 2 (run-time out_dim path)
+    ("euclid", 1, 33, 256, 8, 32, 2, 32, 4, 0.03),       # tensor-core tail: fewer rows than one round, hidden width 32, out_dim 4
 ])
 def test_decoder_tail_matches_oracle(variant, sd, N, M, B, D, H, Cw, O, q, cuda_device, host_scale_map):
     import position_induced_transformer_b200.pit as pit_mod
