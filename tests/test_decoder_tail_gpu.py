@@ -93,5 +93,5 @@ def test_pit_decoder_uses_the_fused_tail(cuda_device, host_scale_map):
         pit_mod.use_fused_decoder_tail(True)
     finally:
         torch.set_float32_matmul_precision(prev)
-    assert 1 <= fused_launches <= 2          # the tail kernel (+ the row statistics if this mesh pair was not cached yet)
+    assert 1 <= fused_launches <= 3          # scale map + tail kernel (+ the row statistics if this mesh pair was not cached yet)
     assert rel_linf(fused, plain) <= 1e-5
