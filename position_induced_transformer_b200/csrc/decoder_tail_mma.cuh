@@ -454,7 +454,7 @@ struct TmBwdSmem {
   float* red;            // [TM_MAX_WARPS]
   int16_t* map;          // [M] column -> slot (-1: unbound)
   int16_t* slot_j;       // [n_slots] slot -> column (-1: free)
-  uint8_t* touched;      // [M]
+  uint32_t* touched;     // [M] columns that are candidates of a tile of the current round (set with atomicOr: several warps may mark one)
   uint8_t* evict;        // [n_slots]
   int* ctl;              // [0] columns needing a slot, [1] [2] free-slot bit masks, [3] bind counter
 };
@@ -462,7 +462,7 @@ struct TmBwdSmem {
 __host__ __device__ inline size_t tm_bwd_smem_bytes(int nh, int M, int W, int C, int O, int n_slots, int threads) {
   return TM_BWD_ROUND * (tm_tile_bytes(nh, true) + tm_cand_bytes(M)) + tm_align((size_t)n_slots * nh * W * 4) +
          tm_align((size_t)(1 + O) * TM_TPC * threads * 4) + 2 * tm_align((size_t)C * (1 + O) * 4) + 64 + tm_align((size_t)M * 2) +
-         tm_align((size_t)n_slots * 2) + tm_align(M) + tm_align(n_slots) + 16;
+         tm_align((size_t)n_slots * 2) + tm_align((size_t)M * 4) + tm_align(n_slots) + 16;
 }
 
 __device__ inline TmBwdSmem tm_bwd_carve(unsigned char* p, int nh, int M, int W, int C, int O, int n_slots, int threads) {
@@ -485,8 +485,8 @@ __device__ inline TmBwdSmem tm_bwd_carve(unsigned char* p, int nh, int M, int W,
   p += tm_align((size_t)M * 2);
   s.slot_j = reinterpret_cast<int16_t*>(p);
   p += tm_align((size_t)n_slots * 2);
-  s.touched = reinterpret_cast<uint8_t*>(p);
-  p += tm_align(M);
+  s.touched = reinterpret_cast<uint32_t*>(p);
+  p += tm_align((size_t)M * 4);
   s.evict = reinterpret_cast<uint8_t*>(p);
   p += tm_align(n_slots);
   s.ctl = reinterpret_cast<int*>(p);
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
         }
       }
       if (nkb > 0) tm_block_finish<NH>(cnt, 0, lane, &T->p[0][0][0], &T->z[0][0][0], inv, m);
-      for (int k = lane; k < cnt; k += 32) S.touched[cand[k]] = 1;
+      for (int k = lane; k < cnt; k += 32) atomicOr(&S.touched[cand[k]], 1u);
       if (lane == 0) T->cnt = cnt;
     }
     __syncthreads();
