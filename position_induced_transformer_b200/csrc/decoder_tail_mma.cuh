@@ -250,16 +250,20 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const fl
     const int ja = ka < cnt ? (int)cand[ka] : 0, jb = kc < cnt ? (int)cand[kc] : 0;
     const float* ra0 = y_chunk + (size_t)ja * NH * C;
     const float* rb0 = y_chunk + (size_t)jb * NH * C;
+    // the loads of every head are issued before the first MMA of the step
+    float2 ya[NH][TM_MT], yb[NH][TM_MT];
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
       const float2* ra = reinterpret_cast<const float2*>(ra0 + h * C);
       const float2* rb = reinterpret_cast<const float2*>(rb0 + h * C);
-      float2 ya[TM_MT], yb[TM_MT];
 #pragma unroll
       for (int mt = 0; mt < TM_MT; ++mt) {
-        ya[mt] = __ldg(ra + mt);
-        yb[mt] = __ldg(rb + mt);
+        ya[h][mt] = __ldg(ra + mt);
+        yb[h][mt] = __ldg(rb + mt);
       }
+    }
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
       uint32_t bh[2][2], bl[2][2];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
@@ -271,7 +275,7 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const fl
       // split terms outermost: the dependent MMAs on one accumulator are eight instructions apart
 #pragma unroll
       for (int mt = 0; mt < TM_MT; ++mt) {
-        const uint32_t al[4] = {tm_trunc_lo(ya[mt].x), tm_trunc_lo(ya[mt].y), tm_trunc_lo(yb[mt].x), tm_trunc_lo(yb[mt].y)};
+        const uint32_t al[4] = {tm_trunc_lo(ya[h][mt].x), tm_trunc_lo(ya[h][mt].y), tm_trunc_lo(yb[h][mt].x), tm_trunc_lo(yb[h][mt].y)};
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) mma_tf32_16x8x8(acc[mt][nt], al, bh[nt]);
       }
@@ -279,7 +283,7 @@ __device__ __forceinline__ void tm_mma_block(float (&acc)[TM_MT][2][4], const fl
       for (int term = 0; term < 2; ++term) {
 #pragma unroll
         for (int mt = 0; mt < TM_MT; ++mt) {
-          const uint32_t ah[4] = {__float_as_uint(ya[mt].x), __float_as_uint(ya[mt].y), __float_as_uint(yb[mt].x), __float_as_uint(yb[mt].y)};
+          const uint32_t ah[4] = {__float_as_uint(ya[h][mt].x), __float_as_uint(ya[h][mt].y), __float_as_uint(yb[h][mt].x), __float_as_uint(yb[h][mt].y)};
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt) mma_tf32_16x8x8(acc[mt][nt], ah, term == 0 ? bl[nt] : bh[nt]);
         }
@@ -329,6 +333,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
   const int tile_end = min(n_tiles, tile_begin + P.rows_per_unit);
   const int c0 = (TM_TPC * g) % P.C;  // this thread's hidden channels (the same in every chunk: C divides the chunk width)
   const int group = P.C / TM_TPC;     // consecutive g sharing a sample
+  const int log2c = 31 - __clz(P.C);
   int round = 0;
   for (int tb = tile_begin; tb < tile_end; tb += nwarps, ++round) {
     const int in_round = min(nwarps, tile_end - tb);
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(cons
       for (int ch0 = 0; ch0 < chunks; ch0 += nwarps) {
         const int chunk = ch0 + warp;
         const bool active = chunk < chunks;
-        const int b = active ? (chunk * TM_CHUNK + TM_TPC * g) / P.C : 0;
+        const int b = active ? (chunk * TM_CHUNK + TM_TPC * g) >> log2c : 0;
         const float* y_chunk = P.y + (size_t)b * P.M * NH * P.C + c0;
         float acc[TM_MT][2][4];
 #pragma unroll
