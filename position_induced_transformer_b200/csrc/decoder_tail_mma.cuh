@@ -307,7 +307,7 @@ __host__ __device__ inline size_t tm_fwd_smem_bytes(int nh, int M, int C, int O,
 // ---------------------------------------------------------------------------------------
 // NO: compile-time bound on out_dim -- 1 (the scalar-output models) or TAIL_MAX_OUT (any out_dim, decided at run time).
 template <int GEO, int CPL, int NH, int NO>
-__global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_fwd_kernel(const TailParams P) {
+__global__ void __launch_bounds__(32 * TM_MAX_WARPS, 3) tail_mma_fwd_kernel(const TailParams P) {
   const int n_out = NO == 1 ? 1 : P.O;
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TmTile<NH, false>;

@@ -411,15 +411,14 @@ bool tail_mma_eligible(const pit_problem_t* p, int out_dim) {
   return tail_mma_enabled() && tail_eligible(p, out_dim) && (c == 32 || c == 64) && ((int64_t)p->batch * c) % pit::TM_CHUNK == 0;
 }
 
-// rows_per_unit counts 16-row tiles per CTA; one 64-column chunk per warp, at most 8 warps.  Large meshes get whole
-// rounds per CTA; small ones (fewer tiles than CTA slots x round) get one CTA per few tiles instead -- more SMs beat full rounds.
-void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c, int round) {
+// rows_per_unit counts 16-row tiles per CTA; one 64-column chunk per warp, at most 8 warps.  Equal shares for
+// `ctas_per_sm` resident CTAs per SM (a last, partly filled round costs less than an unbalanced wave).
+void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c, int ctas_per_sm) {
   const int chunks = p->batch * p->dim / pit::TM_CHUNK;
   c.threads = chunks <= 4 ? 128 : 256;
   const int tiles = (p->n_out + pit::TM_ROWS - 1) / pit::TM_ROWS;
-  const int target = sm_count() * 2;
-  int per_cta = (tiles + target - 1) / target;
-  if (per_cta >= round) per_cta = (per_cta + round - 1) / round * round;
+  const int target = sm_count() * ctas_per_sm;
+  const int per_cta = (tiles + target - 1) / target;
   c.rows_per_unit = per_cta;
   c.grid = (tiles + per_cta - 1) / per_cta;
   c.cpl = cpl_of(p->n_in);
@@ -428,7 +427,7 @@ void plan_tail_mma_grid(const pit_problem_t* p, TallPlan& c, int round) {
 TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
   TallPlan c{};
   if (!tail_mma_eligible(p, out_dim)) return c;
-  plan_tail_mma_grid(p, c, pit::TM_MAX_WARPS);
+  plan_tail_mma_grid(p, c, 3);  // 80 registers per thread: three CTAs of 8 warps per SM
   c.smem = pit::tm_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim, c.threads);
   if (c.smem > (size_t)max_smem_optin() - 1024) return c;
   c.ok = true;
@@ -438,7 +437,7 @@ TallPlan plan_tail_mma_fwd(const pit_problem_t* p, int out_dim) {
 TallPlan plan_tail_mma_bwd(const pit_problem_t* p, int out_dim) {
   TallPlan c{};
   if (!tail_mma_eligible(p, out_dim)) return c;
-  plan_tail_mma_grid(p, c, pit::TM_BWD_ROUND);
+  plan_tail_mma_grid(p, c, 2);
   const int W = p->batch * p->dim;
   const size_t fixed = pit::tm_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, 0, c.threads);
   const size_t per_slot = (size_t)p->n_head * W * 4 + 2;
