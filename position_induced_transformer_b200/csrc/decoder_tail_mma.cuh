@@ -663,7 +663,8 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
       if (lane == 0) T->cnt = cnt;
     }
     __syncthreads();
-    tm_bind_slots<NH>(P, S, W, log2c);  // ends with the bindings visible to every thread; its trailing resets only concern the next phase 1
+    tm_bind_slots<NH>(P, S, W, log2c);
+    __syncthreads();
     // ---- phase 2 ----
     for (int v = 0; v < in_round; ++v) {
       Tile* T = reinterpret_cast<Tile*>(S.tiles + v * tile_stride);
