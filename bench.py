@@ -351,10 +351,46 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
 
+    # ---- forward only (inference): the same batches through model + loss under no_grad, replayed as a graph ----
+    fwd_ms = None
+    if use_graph:
+        static_in = tuple(x.clone() for x in resident[0][0])
+        static_tgt = resident[0][1].clone()
+        with torch.no_grad():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    forward_loss(static_in, static_tgt)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            fgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(fgraph):
+                floss = forward_loss(static_in, static_tgt)
+
+            def fwd_step(ins, target):
+                for dst, src in zip(static_in, ins):
+                    dst.copy_(src, non_blocking=True)
+                static_tgt.copy_(target, non_blocking=True)
+                fgraph.replay()
+                return floss
+
+            for i in range(min(args.warmup, 5)):
+                fwd_step(*resident[i % n_buf])
+            barrier()
+            f_start, f_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f_start.record()
+            for i in range(args.steps):
+                fwd_step(*resident[i % n_buf])
+            f_end.record()
+            barrier()
+            fwd_ms = f_start.elapsed_time(f_end)
+
     if world > 1:
-        tms = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        tms = torch.tensor([ms, e2e_ms, fwd_ms or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(tms[0]), float(tms[1])
+        fwd_ms = float(tms[2]) if fwd_ms is not None else None
     if rank != 0:
         return
 
@@ -392,6 +428,8 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic", "config": bench_config(args, batch),
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
+        "forward_only": None if fwd_ms is None else {"value": batch * world * args.steps / (fwd_ms * 1e-3), "unit": UNIT,
+                                                     "ms_per_step": fwd_ms / args.steps, "what": "forward + loss under no_grad, device-resident inputs"},
         "gpu_launches": launches, "eager_ms_per_step": eager_ms, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info, "kernels": kernel_table[:8],
     }
     print(json.dumps(line), flush=True)
