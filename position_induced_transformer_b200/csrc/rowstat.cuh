@@ -27,6 +27,56 @@ struct RowstatParams {
   int k_lo, k_hi;
 };
 
+// k_lo-th and k_hi-th (k_hi in {k_lo, k_lo + 1}) smallest of the warp's 32 x RR keys (unused entries 0xffffffff).
+template <int RR>
+__device__ __forceinline__ void rowstat_select(const uint32_t (&key)[RR], int k_lo, int k_hi, uint32_t& lo_out, uint32_t& hi_out) {
+  // k_lo-th smallest key, most significant bit first.  `cand` counts the keys that still match the decided
+  // bits; once a single candidate is left it is the answer and the remaining bit steps are skipped (on meshes
+  // without exact ties this happens after ~log2(M) + a few steps instead of 32).
+  uint32_t prefix = 0;
+  int k = k_lo;
+  int cand = RR * 32;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < RR; ++r) c += (((key[r] ^ prefix) >> bit) == 0u) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (k >= c) {
+      k -= c;
+      prefix |= 1u << bit;
+      cand -= c;
+    } else {
+      cand = c;
+    }
+    if (cand == 1 && bit > 0) {
+      // the unique key that agrees with `prefix` on bits [bit, 31]
+      uint32_t mine = 0;
+#pragma unroll
+      for (int r = 0; r < RR; ++r)
+        if (((key[r] ^ prefix) >> bit) == 0u) mine = key[r];
+      prefix = __reduce_or_sync(FULL, mine);
+      break;
+    }
+  }
+  const uint32_t lo = prefix;
+  uint32_t hi = lo;
+  if (k_hi != k_lo) {  // k_hi == k_lo + 1
+    int le = 0;
+    uint32_t gt = 0xffffffffu;
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+      le += (key[r] <= lo) ? 1 : 0;
+      if (key[r] > lo) gt = min(gt, key[r]);
+    }
+    le = __reduce_add_sync(FULL, le);
+    gt = __reduce_min_sync(FULL, gt);
+    if (k_hi >= le) hi = gt;
+  }
+  lo_out = lo;
+  hi_out = hi;
+}
+
 template <int GEO, int R>
 __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -49,49 +99,41 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
   for (int r = 1; r < R; ++r) mn = min(mn, key[r]);
   mn = __reduce_min_sync(FULL, mn);
 
-  // k_lo-th smallest key, most significant bit first.  `cand` counts the keys that still match the decided
-  // bits; once a single candidate is left it is the answer and the remaining bit steps are skipped (on meshes
-  // without exact ties this happens after ~log2(M) + a few steps instead of 32).
-  uint32_t prefix = 0;
-  int k = P.k_lo;
-  int cand = R * 32;
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    int c = 0;
+  uint32_t lo, hi;
+  bool done = false;
+  // Small ranks (the locality masks keep a few dozen columns at most): shrink the problem before selecting.  The
+  // (k_hi+1)-th smallest of the 32 per-lane minima is an upper bound T of the k_hi-th smallest key (those lanes hold
+  // k_hi+1 distinct keys <= T), so only keys <= T can matter; a lane usually holds 0..3 of them.  They are compacted
+  // into four registers per lane and the bit-serial selection runs on 4 instead of R keys per lane.  Rows where some
+  // lane holds more than four (heavy ties) take the full path below -- same result either way.
+  if (P.k_hi < 32) {
+    uint32_t lm = key[0];
 #pragma unroll
-    for (int r = 0; r < R; ++r) c += (((key[r] ^ prefix) >> bit) == 0u) ? 1 : 0;
-    c = __reduce_add_sync(FULL, c);
-    if (k >= c) {
-      k -= c;
-      prefix |= 1u << bit;
-      cand -= c;
-    } else {
-      cand = c;
+    for (int r = 1; r < R; ++r) lm = min(lm, key[r]);
+    int rank = 0;  // position of this lane's minimum among the 32 (ties broken by lane index)
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t other = __shfl_sync(FULL, lm, l);
+      rank += (other < lm || (other == lm && l < lane)) ? 1 : 0;
     }
-    if (cand == 1 && bit > 0) {
-      // the unique key that agrees with `prefix` on bits [bit, 31]
-      uint32_t mine = 0;
+    const unsigned owner = __ballot_sync(FULL, rank == P.k_hi);
+    const uint32_t bound = __shfl_sync(FULL, lm, __ffs(owner) - 1);
+    if (bound != 0xffffffffu) {  // fewer than k_hi+1 lanes with a valid key: no bound, full path
+      uint32_t c[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      int n = 0;
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (((key[r] ^ prefix) >> bit) == 0u) mine = key[r];
-      prefix = __reduce_or_sync(FULL, mine);
-      break;
+      for (int r = 0; r < R; ++r) {
+        if (key[r] <= bound) {
+          c[3] = c[2], c[2] = c[1], c[1] = c[0], c[0] = key[r];
+          ++n;
+        }
+      }
+      if (!__any_sync(FULL, n > 4)) {
+        rowstat_select<4>(c, P.k_lo, P.k_hi, lo, hi);
+        done = true;
+      }
     }
   }
-  const uint32_t lo = prefix;
-  uint32_t hi = lo;
-  if (P.k_hi != P.k_lo) {  // k_hi == k_lo + 1
-    int le = 0;
-    uint32_t gt = 0xffffffffu;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      le += (key[r] <= lo) ? 1 : 0;
-      if (key[r] > lo) gt = min(gt, key[r]);
-    }
-    le = __reduce_add_sync(FULL, le);
-    gt = __reduce_min_sync(FULL, gt);
-    if (P.k_hi >= le) hi = gt;
-  }
+  if (!done) rowstat_select<R>(key, P.k_lo, P.k_hi, lo, hi);
   if (lane == 0) {
     P.v_min[row] = __uint_as_float(mn);
     P.v_lo[row] = __uint_as_float(lo);

@@ -39,6 +39,40 @@ def test_rowstat_is_bit_exact(name, cuda_device):
         assert (k_lo, k_hi, w) == po.quantile_ranks(q, mi.shape[-2])
 
 
+@pytest.mark.parametrize("case", ["random", "few_columns", "duplicates", "lattice_ties", "rank_31", "rank_32", "batched"])
+def test_rowstat_small_rank_path_is_bit_exact(case, cuda_device):
+    """The candidate-compaction path of the warp kernel (k_hi < 32) and its fall-backs (too few lanes with keys, more than
+    four candidates in a lane) against a full sort."""
+    from position_induced_transformer_b200 import _cabi, posatt
+    g = torch.Generator().manual_seed(11)
+    n, m, q = 300, 700, 0.02
+    mo, mi = torch.rand(n, 2, generator=g), torch.rand(m, 2, generator=g)
+    if case == "few_columns":
+        m, q = 20, 0.4                                   # fewer valid keys than lanes: no bound, full path
+        mi = torch.rand(m, 2, generator=g)
+    elif case == "duplicates":
+        mi = mi[torch.randint(0, 40, (m,), generator=g)]  # 40 distinct points: every distance 17-fold tied
+    elif case == "lattice_ties":
+        ax = torch.linspace(0, 1, 26)
+        mi = torch.stack(torch.meshgrid(ax, ax, indexing="ij"), -1).reshape(-1, 2)
+        mo = mi[::3].clone()                              # rows sit on lattice points: 4- and 8-fold ties
+        m = mi.shape[0]
+    elif case == "rank_31":
+        q = 30.5 / (m - 1)
+    elif case == "rank_32":
+        q = 31.5 / (m - 1)                               # k_hi = 32: just outside the small-rank path
+    elif case == "batched":
+        mo, mi = torch.rand(3, n, 2, generator=g), torch.rand(3, m, 2, generator=g)
+    d2 = po.sqdist(mo, mi, "euclid")
+    k_lo, k_hi, w = _cabi.quantile_ranks(q, m)
+    ref = po.exact_rowstat(d2, k_lo, k_hi)
+    vals = torch.zeros((mi.shape[0] if mi.dim() == 3 else 1), m, 4, device=cuda_device)
+    st = posatt._Stage(mo.to(cuda_device), mi.to(cuda_device), vals, 1, "euclid")
+    got = posatt.row_statistics(st, mo.to(cuda_device), mi.to(cuda_device), None, q)
+    for a, b in zip(got[:3], ref):
+        assert torch.equal(a.cpu(), b)
+
+
 @pytest.mark.parametrize("name", golden_names("op_"))
 def test_forward_backward_match_reference(name, cuda_device):
     g = load_golden("op_" + name)
