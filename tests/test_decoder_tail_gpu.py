@@ -42,6 +42,8 @@ def _case(variant, sd, N, M, B, D, H, Cw, O, q, seed):
     ("euclid", 2, 600, 700, 2, 16, 2, 64, 1, 0.01),      # tensor-core tail with 32 columns per lane (M > 256)
     ("periodic2d", 2, 1024, 64, 2, 32, 2, 64, 2, 0.1),   # tensor-core tail, periodic distance, out_dim 2 (run-time out_dim path)
     ("euclid", 1, 33, 256, 8, 32, 2, 32, 4, 0.03),       # tensor-core tail: fewer rows than one round, hidden width 32, out_dim 4
+    ("euclid", 2, 5, 6, 2, 8, 1, 32, 1, 0.5),            # tensor-core tail at its smallest: one tile, one chunk, six columns
+    ("euclid", 2, 1000, 9, 1, 4, 2, 64, 1, 0.3),         # one sample, nine latent points
 ])
 def test_decoder_tail_matches_oracle(variant, sd, N, M, B, D, H, Cw, O, q, cuda_device, host_scale_map):
     import position_induced_transformer_b200.pit as pit_mod
