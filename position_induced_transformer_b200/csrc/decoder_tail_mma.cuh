@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 3) tail_mma_fwd_kernel(cons
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = par[c0 + 2 * mt + (e >> 1)];  // the accumulators start from the bias b1
         for (int kb = 0; kb < nkb; ++kb) {
           if (nkb > 1) {  // rare: the candidate list spans several blocks -> rebuild block kb in place (CTA-uniform branch)
             __syncthreads();
@@ -414,12 +414,11 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 3) tail_mma_fwd_kernel(cons
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int c = c0 + 2 * mt + half;
-            const float bias = par[c];
             float hid[4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-              for (int e = 0; e < 2; ++e) hid[nt * 2 + e] = tm_gelu(acc[mt][nt][half * 2 + e] + bias);
+              for (int e = 0; e < 2; ++e) hid[nt * 2 + e] = tm_gelu(acc[mt][nt][half * 2 + e]);
 #pragma unroll
             for (int o = 0; o < NO; ++o) {
               if (o < n_out) {
@@ -684,7 +683,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = S.par[c0 + 2 * mt + (e >> 1)];  // start from the bias b1
         // (a) hidden pre-activation, as in the forward
         for (int kb = 0; kb < nkb; ++kb) {
           if (nkb > 1) {
@@ -712,7 +711,6 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
             for (int half = 0; half < 2; ++half) {
               const int i = 2 * mt + half;
               const int c = c0 + i;
-              const float bias = S.par[c];
               float wv[NO], dw[NO];
 #pragma unroll
               for (int o = 0; o < NO; ++o) {
@@ -723,7 +721,7 @@ __global__ void __launch_bounds__(32 * TM_MAX_WARPS, 2) tail_mma_bwd_kernel(cons
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float hid, dhid;
-                tm_gelu_pair(acc[mt][q >> 1][half * 2 + (q & 1)] + bias, hid, dhid);
+                tm_gelu_pair(acc[mt][q >> 1][half * 2 + (q & 1)], hid, dhid);
                 float up = 0.f;
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
