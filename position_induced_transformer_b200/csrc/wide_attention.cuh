@@ -109,7 +109,7 @@ __device__ __forceinline__ unsigned wide_rows_to_visit(const WideBox<GEO>& bx, c
 }
 
 template <int GEO, int NH, int WPAD>
-__global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams P) {
+__global__ void __launch_bounds__(WIDE_THREADS, 3) wide_fwd_kernel(const WideParams P) {
   extern __shared__ __align__(16) unsigned char wide_smem_raw[];
   const int rw = wide_row_words(NH);
   float* rowtab = reinterpret_cast<float*>(wide_smem_raw);
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) wide_fwd_kernel(const WideParams
 }
 
 template <int GEO, int NH, int WPAD>
-__global__ void __launch_bounds__(WIDE_THREADS) wide_dscale_kernel(const WideParams P) {
+__global__ void __launch_bounds__(WIDE_THREADS, 3) wide_dscale_kernel(const WideParams P) {
   extern __shared__ __align__(16) unsigned char wide_smem_raw[];
   const int rw = wide_row_words(NH);
   float* rowtab = reinterpret_cast<float*>(wide_smem_raw);
