@@ -11,6 +11,7 @@
  *   pit_posatt_backward     what autograd replays for the above   (no explicit code in the reference)
  *   pit_head_scale*         the scale map tan(c*(1+sin(lmda)))    pit.py:48, 135, 196, 254
  *   pit_bias_act*           bias + GELU epilogues of the MLPs     pit.py:21-26, 111, 121
+ *   pit_rel_lp*             the training loss RelLpNorm           utils.py:60-98
  *
  * Conventions
  *   - all tensors are fp32, contiguous, row-major, resident on the CURRENT CUDA device;
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 3
+#define PIT_ABI_VERSION 4
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -131,6 +132,16 @@ int pit_bias_act_forward(const float* z, const float* bias, float* out, int64_t 
                          void* stream);
 int pit_bias_act_backward(const float* z, const float* bias, const float* d_out, float* d_z, float* d_bias, int64_t rows,
                           int32_t cols, int32_t apply_gelu, void* stream);
+
+/* Relative Lp error of the reference's utils.py:60-98 (RelLpNorm):
+ *   loss = sum_b (1/O) sum_o ||truth[b,:,o] - pred[b,:,o]||_p / ||truth[b,:,o]||_p,   p = 1 or 2, O <= 4,
+ * truth / pred [B, L, O].  norms [B, O, 2] receives (||e||_p, ||truth||_p) and is consumed by the backward, which
+ * writes d_pred = d_loss * d loss / d pred (d_loss: device scalar). */
+int pit_rel_lp_supported(int32_t batch, int64_t length, int32_t out_dim, int32_t p);
+int pit_rel_lp_forward(const float* truth, const float* pred, int32_t batch, int64_t length, int32_t out_dim, int32_t p,
+                       float* norms, float* loss, void* stream);
+int pit_rel_lp_backward(const float* truth, const float* pred, const float* norms, const float* d_loss, int32_t batch,
+                        int64_t length, int32_t out_dim, int32_t p, float* d_pred, void* stream);
 
 /* Fused decoder tail: pit.decoder (pit.py:124-127) = cross position-attention `up` + kaiming_mlp `de`
  * (pit.py:21-26), for shared meshes with M <= 1024, H <= 2, hidden width C a power of two in [32, 512], out_dim <= 4.

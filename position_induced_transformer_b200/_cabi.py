@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = (
     "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
@@ -21,6 +21,7 @@ EXPORTS = (
     "pit_decoder_tail_supported", "pit_decoder_tail_forward", "pit_decoder_tail_backward",
     "pit_head_scale_forward", "pit_head_scale_backward",
     "pit_bias_act_supported", "pit_bias_act_forward", "pit_bias_act_backward",
+    "pit_rel_lp_supported", "pit_rel_lp_forward", "pit_rel_lp_backward",
 )
 
 
@@ -62,6 +63,9 @@ def _load() -> C.CDLL:
     lib.pit_bias_act_supported.argtypes = [i64, i32]
     lib.pit_bias_act_forward.argtypes = [f32p, f32p, f32p, i64, i32, i32, p]
     lib.pit_bias_act_backward.argtypes = [f32p, f32p, f32p, f32p, f32p, i64, i32, i32, p]
+    lib.pit_rel_lp_supported.argtypes = [i32, i64, i32, i32]
+    lib.pit_rel_lp_forward.argtypes = [f32p, f32p, i32, i64, i32, i32, f32p, f32p, p]
+    lib.pit_rel_lp_backward.argtypes = [f32p, f32p, f32p, f32p, i32, i64, i32, i32, f32p, p]
     if lib.pit_abi_version() != ABI_VERSION:
         raise ImportError(f"libpit_posatt.so ABI {lib.pit_abi_version()} != expected {ABI_VERSION}; rebuild it")
     return lib

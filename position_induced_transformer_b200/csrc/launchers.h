@@ -9,6 +9,7 @@
 #include "dense_attention.cuh"
 #include "local_attention.cuh"
 #include "mlp_epilogue.cuh"
+#include "rel_lp_loss.cuh"
 #include "rowstat.cuh"
 #include "tall_attention.cuh"
 #include "wide_attention.cuh"
@@ -49,6 +50,8 @@ cudaError_t tail_mma_backward(int geo, const TallPlan& plan, const TailParams& P
 int wide_pad(int width);
 cudaError_t wide_forward(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
 cudaError_t wide_dscale(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
+// tu_loss.cu  (stage 0: partial sums, 1: finalize, 2: backward)
+cudaError_t rel_lp(int stage, const LossParams& P, int grid_x, cudaStream_t st);
 // tu_mlp_epilogue.cu
 cudaError_t bias_act(bool backward, const EpiParams& P, int grid, cudaStream_t st);
 // tu_dense.cu  (mode: DENSE_FWD / DENSE_DSCALE / DENSE_DVALUES; nv: 64, 128 or 256 value columns per tile)

@@ -811,6 +811,48 @@ int pit_head_scale_backward(const float* lmda, const float* scale, const float* 
   return PIT_OK;
 }
 
+int pit_rel_lp_supported(int32_t batch, int64_t length, int32_t out_dim, int32_t p) {
+  return batch >= 1 && batch <= 65535 && length >= 1 && out_dim >= 1 && out_dim <= pit::LOSS_MAX_OUT && (p == 1 || p == 2) ? 1 : 0;
+}
+
+namespace {
+// blocks along one sample: enough to fill the chip together with the batch, total thread count a multiple of out_dim
+int rel_lp_grid(int batch, int64_t length, int out_dim) {
+  const int64_t n = length * out_dim;
+  int64_t blocks = (n + pit::LOSS_THREADS * 8 - 1) / (pit::LOSS_THREADS * 8);
+  const int64_t cap = ((int64_t)sm_count() * 8 + batch - 1) / batch;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  while ((blocks * pit::LOSS_THREADS) % out_dim != 0) ++blocks;   // out_dim 3: a multiple of three blocks
+  return (int)blocks;
+}
+}  // namespace
+
+int pit_rel_lp_forward(const float* truth, const float* pred, int32_t batch, int64_t length, int32_t out_dim, int32_t p,
+                       float* norms, float* loss, void* stream) {
+  if (!truth || !pred || !norms || !loss || !pit_rel_lp_supported(batch, length, out_dim, p)) return fail(PIT_ERR_ARG, "rel_lp: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pit::LossParams P{};
+  P.truth = truth, P.pred = pred, P.sums = norms, P.loss = loss, P.L = length, P.B = batch, P.O = out_dim, P.p = p;
+  PIT_CUDA(cudaMemsetAsync(norms, 0, (size_t)batch * out_dim * 2 * sizeof(float), st));
+  PIT_CUDA(launch::rel_lp(0, P, rel_lp_grid(batch, length, out_dim), st));
+  PIT_CUDA(launch::rel_lp(1, P, 1, st));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
+int pit_rel_lp_backward(const float* truth, const float* pred, const float* norms, const float* d_loss, int32_t batch,
+                        int64_t length, int32_t out_dim, int32_t p, float* d_pred, void* stream) {
+  if (!truth || !pred || !norms || !d_loss || !d_pred || !pit_rel_lp_supported(batch, length, out_dim, p))
+    return fail(PIT_ERR_ARG, "rel_lp: bad arguments");
+  pit::LossParams P{};
+  P.truth = truth, P.pred = pred, P.sums = const_cast<float*>(norms), P.d_loss = d_loss, P.d_pred = d_pred, P.L = length, P.B = batch,
+  P.O = out_dim, P.p = p;
+  PIT_CUDA(launch::rel_lp(2, P, rel_lp_grid(batch, length, out_dim), static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
 int pit_bias_act_supported(int64_t rows, int32_t cols) {
   return rows >= 1 && cols >= 4 && cols % 4 == 0 && pit::EPI_THREADS % (cols / 4) == 0 ? 1 : 0;
 }

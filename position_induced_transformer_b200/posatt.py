@@ -399,6 +399,49 @@ def bias_act(z: torch.Tensor, bias: torch.Tensor, apply_gelu: bool) -> torch.Ten
 
 
 # ----------------------------------------------------------------------------------------------
+# relative Lp loss (utils.py:60-98): partial sums + finalize forward, one elementwise pass backward
+# ----------------------------------------------------------------------------------------------
+class _RelLp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, truth, p):
+        pred, truth = pred.contiguous(), truth.contiguous()      # (B, L, O)
+        B, L, O = pred.shape
+        norms = torch.empty((B, O, 2), dtype=torch.float32, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            _cabi.check(_cabi.lib.pit_rel_lp_forward(truth.data_ptr(), pred.data_ptr(), B, L, O, int(p), norms.data_ptr(),
+                                                     loss.data_ptr(), _stream(pred.device)), "pit_rel_lp_forward")
+        ctx.save_for_backward(pred, truth, norms)
+        ctx.p = int(p)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        pred, truth, norms = ctx.saved_tensors
+        B, L, O = pred.shape
+        d_loss = d_loss.contiguous()
+        d_pred = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            _cabi.check(_cabi.lib.pit_rel_lp_backward(truth.data_ptr(), pred.data_ptr(), norms.data_ptr(), d_loss.data_ptr(), B, L, O,
+                                                      ctx.p, d_pred.data_ptr(), _stream(pred.device)), "pit_rel_lp_backward")
+        return d_pred, None, None
+
+
+@torch.compiler.disable
+def rel_lp_supported(truth: torch.Tensor, pred: torch.Tensor, p) -> bool:
+    """True when the fused loss covers this case: float32 CUDA tensors (B, L, O) with O <= 4, p in {1, 2}, no gradient to `truth`."""
+    return (pred.is_cuda and truth.is_cuda and pred.dtype == torch.float32 and truth.dtype == torch.float32 and pred.dim() == 3
+            and pred.shape == truth.shape and not truth.requires_grad and p in (1, 2) and pred.numel() > 0
+            and bool(_cabi.lib.pit_rel_lp_supported(pred.shape[0], pred.shape[1], pred.shape[2], int(p))))
+
+
+@torch.compiler.disable
+def rel_lp_loss(truth: torch.Tensor, pred: torch.Tensor, p) -> torch.Tensor:
+    """sum_b mean_o ||truth - pred||_p / ||truth||_p over (B, L, O) tensors; gradient flows to `pred`."""
+    return _RelLp.apply(pred, truth, int(p))
+
+
+# ----------------------------------------------------------------------------------------------
 # fused decoder tail: cross position-attention + two-layer MLP (pit.decoder, pit.py:124-127)
 # ----------------------------------------------------------------------------------------------
 class _DecoderTail(torch.autograd.Function):

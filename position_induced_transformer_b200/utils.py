@@ -1,7 +1,8 @@
 """Drop-in for the reference ``utils.py``: losses, parameter count and the pixel-wise normaliser.
 
 Same names and call semantics (``RelLpNorm(out_dim, p)(true, pred)`` etc., utils.py:6-98); these sit
-outside the position-attention hot path and are ordinary torch code.
+outside the position-attention hot path and are ordinary torch code -- except that ``RelLpNorm`` on CUDA float32
+tensors with p in {1, 2} runs as three launches of libpit_posatt.so instead of ~14 torch kernels.
 """
 import operator
 from functools import reduce
@@ -41,6 +42,15 @@ class RelLpNorm(_RelativeError):
 
     def _magnitude(self, x):
         return torch.norm(x, p=self._ord, dim=1)
+
+    def __call__(self, true, pred):
+        t = true.reshape(true.size(0), -1, self._out_dim)
+        q = pred.reshape(pred.size(0), -1, self._out_dim)
+        if q.is_cuda:
+            from .posatt import rel_lp_loss, rel_lp_supported       # the CUDA library is only needed for CUDA tensors
+            if rel_lp_supported(t, q, self._ord):
+                return rel_lp_loss(t, q, self._ord)
+        return super().__call__(true, pred)
 
 
 class RelMaxNorm(_RelativeError):

@@ -66,3 +66,23 @@ def test_kaiming_mlp_fused_equals_plain(cuda_device):
     assert rel_linf(res[True][1], res[False][1]) <= 1e-5
     for a, b in zip(res[True][2], res[False][2]):
         assert rel_linf(a, b) <= 1e-5
+
+
+@pytest.mark.parametrize("shape,p", [((8, 1849, 1), 2), ((8, 1024, 1), 1), ((3, 2048, 3), 2), ((2, 500, 4), 1), ((20, 11271, 4), 2),
+                                     ((1, 7, 2), 2)])
+def test_rel_lp_loss_matches_torch(shape, p, cuda_device):
+    """Fused RelLpNorm (utils.py:60-98) against the torch expression it replaces: value and gradient."""
+    from position_induced_transformer_b200 import utils as u
+    g = torch.Generator().manual_seed(sum(shape) + p)
+    true = torch.randn(shape, generator=g).to(cuda_device)
+    pred = (true.cpu() + 0.3 * torch.randn(shape, generator=g)).to(cuda_device)
+    loss_fn = u.RelLpNorm(shape[-1], p)
+    a = pred.clone().requires_grad_(True)
+    b = pred.clone().requires_grad_(True)
+    got = loss_fn(true, a)
+    want = (torch.norm(true - b, p=p, dim=1) / torch.norm(true, p=p, dim=1)).mean(dim=-1).sum()
+    (3.0 * got).backward()
+    (3.0 * want).backward()
+    assert got.shape == want.shape
+    assert abs(float(got) - float(want)) <= 2e-6 * abs(float(want))
+    assert rel_linf(a.grad, b.grad) <= 1e-5
