@@ -33,6 +33,12 @@ def _worker(rank, world, port, out_dir):
     RelLpNorm(2, 2)(y[mine], model(x[mine])).backward()
     flat.all_reduce()
     torch.save(flat.buffer.clone(), os.path.join(out_dir, f"g{rank}.pt"))
+    # the step the benchmark runs: grads released before backward, packed with one copy, then reduced
+    flat.release()
+    RelLpNorm(2, 2)(y[mine], model(x[mine])).backward()
+    flat.gather()
+    flat.all_reduce()
+    torch.save(flat.buffer.clone(), os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -47,8 +53,9 @@ def test_two_rank_sum_equals_full_batch_gradient(tmp_path):
     flat.zero()
     RelLpNorm(2, 2)(y, model(x)).backward()
     for r in range(2):
-        got = torch.load(os.path.join(str(tmp_path), f"g{r}.pt"))
-        assert torch.allclose(got, flat.buffer, rtol=1e-5, atol=1e-7)
+        for tag in ("g", "r"):          # accumulate-into-views path and release/gather path
+            got = torch.load(os.path.join(str(tmp_path), f"{tag}{r}.pt"))
+            assert torch.allclose(got, flat.buffer, rtol=1e-5, atol=1e-7)
 
 
 def test_shard_range_covers_everything():
