@@ -408,7 +408,10 @@ def run_ours(args, rank, world, local_rank):
                         "kernel": {"call": top[0], "variant": top[1], "mesh_batched": bool(top[2]), "B": top[3], "H": top[4],
                                    "N": top[5], "M": top[6], "D": top[7]},
                         "algorithmic_bytes_per_launch": q, "avg_launch_ms": kernels[top]["ms_avg"],
-                        "share_of_step": share, "peak_source": peak_src}
+                        "share_of_step": share, "peak_source": peak_src,
+                        "note": ("fused decoder tail: `achieved` counts the bytes the unfused attention stage has to move (SURVEY 8d); the kernel "
+                                 "itself keeps them on chip (see `traffic`) and is bound by instruction issue, profiles/r1_v9_ncu_tail_mma.md")
+                        if top[0].startswith("tail") else None}
     kernel_table = sorted(({"call": k[0], "N": k[5], "M": k[6], "D": k[7], "concat": bool(k[9]), "ms_avg": v["ms_avg"],
                             "calls_per_step": v["calls"] / k_steps, "share_of_step": v["ms_total"] / k_steps / (ms / args.steps),
                             "GBps_algorithmic": algorithmic_bytes(k) / (v["ms_avg"] * 1e-3) / 1e9} for k, v in kernels.items()),
