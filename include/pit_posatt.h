@@ -12,6 +12,8 @@
  *   pit_head_scale*         the scale map tan(c*(1+sin(lmda)))    pit.py:48, 135, 196, 254
  *   pit_bias_act*           bias + GELU epilogues of the MLPs     pit.py:21-26, 111, 121
  *   pit_rel_lp*             the training loss RelLpNorm           utils.py:60-98
+ *   pit_decoder_tail*       pit.decoder = up + de MLP, fused      pit.py:124-127, 21-26
+ *   pit_tail_plan*          lambda-independent part of the mask   pit.py:136 (re-sorted every step there)
  *
  * Conventions
  *   - all tensors are fp32, contiguous, row-major, resident on the CURRENT CUDA device;
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 4
+#define PIT_ABI_VERSION 5
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -143,24 +145,60 @@ int pit_rel_lp_forward(const float* truth, const float* pred, int32_t batch, int
 int pit_rel_lp_backward(const float* truth, const float* pred, const float* norms, const float* d_loss, int32_t batch,
                         int64_t length, int32_t out_dim, int32_t p, float* d_pred, void* stream);
 
+/* Tile plan of a decoder stage over shared meshes -- everything about its locality mask that does not depend on lmda.
+ * The reference re-derives the mask from a full row sort in every step (torch.quantile, pit.py:136) although the
+ * meshes never change (train_darcy.py:88-96, 128).  The plan sorts the N rows by their candidate set {j : d2(row, j) <=
+ * v_hi(row) (1 + 1e-6)} (a superset of what any head can keep) and cuts the sorted order into tiles of 32 rows:
+ *   rec      [n_tiles*32] x float4  {v_min, v_lo, v_hi, row index (int32 bit pattern; -1 = padding of the last tile)}
+ *   tile_off [n_tiles+1] int32      offsets of the tiles' candidate lists in `cand`: multiples of 8, so that every list
+ *                                   (and its lines of d2) starts on a 16-byte boundary; n_cand = tile_off[n_tiles]
+ *   tile_cnt [n_tiles] int32        number of candidates of each tile
+ *   cand     [n_cand] int16         candidate columns, ascending inside a tile (then zero padding up to the next offset)
+ *   d2       [n_cand*32] float      squared distance (reference rounding order, pit.py:134 / 193-195 / 251-253) of tile
+ *                                   row r to candidate k of tile t at d2[(tile_off[t] + k)*32 + r]
+ * n_tiles = ceil(N / 32).  Build it once per (mesh_out, mesh_in, locality):
+ *   1. pit_tail_plan_rows   sorts the rows and writes tile_off / tile_cnt; the caller reads tile_off[n_tiles] (one int32, the only
+ *                           device->host read of the library's protocol) and allocates `cand` and `d2`;
+ *   2. pit_tail_plan_fill   writes cand, d2, rec.  Same workspace as step 1, untouched in between.
+ * Requires shared meshes with M <= 1024.  Pass the plan to pit_decoder_tail_forward / _backward (NULL: no plan, the
+ * kernels scan the latent mesh themselves). */
+typedef struct pit_tail_plan {
+  const void* rec;
+  const int32_t* tile_off;
+  const int32_t* tile_cnt;
+  const int16_t* cand;
+  const float* d2;
+  int32_t n_tiles;
+} pit_tail_plan_t;
+
+size_t pit_tail_plan_workspace_bytes(const pit_problem_t* p);
+int pit_tail_plan_rows(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                       const pit_rowstat_t* stat, int32_t* tile_off, int32_t* tile_cnt, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int pit_tail_plan_fill(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                       const pit_rowstat_t* stat, const int32_t* tile_off, void* rec, int16_t* cand, float* d2,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused decoder tail: pit.decoder (pit.py:124-127) = cross position-attention `up` + kaiming_mlp `de`
  * (pit.py:21-26), for shared meshes with M <= 1024, H <= 2, hidden width C a power of two in [32, 512], out_dim <= 4.
  * problem->dim is the hidden width C.  The first Linear is pushed through the (linear) attention by the caller:
  *   y [B,M,H,C]  with  y[b,j,h,:] = W1[:, h*D:(h+1)*D] @ U[b,j,:]        (W1 = de.mlp1.weight, U = latent features)
  *   out[b,n,o]  = b2[o] + sum_c W2[o,c] * gelu(b1[c] + sum_h sum_j A_h[n,j] * y[b,j,h,c])      (exact erf GELU)
- * so nothing of size N x H*D or N x C is ever written to memory.  rowsum [H,N] is saved for the backward, which
+ * so nothing of size N x H*D or N x C is ever written to memory.  rowsum (2*H*ceil32(N) floats, opaque: row sums and,
+ * with a tile plan, the rows' mean squared distances in tile order) is saved for the backward -- pass the same plan --, which
  * returns d_y [B,M,H,C] (dW1 and dU follow from it through the caller's GEMM), d_scale [H], d_b1 [C], d_w2 [O,C],
  * d_b2 [O]; every gradient buffer is overwritten. */
 int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim);
 int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
                              const float* period, const float* y, const float* scale,
                              const pit_rowstat_t* stat, const float* b1, const float* w2, const float* b2,
-                             int32_t out_dim, float* out, float* rowsum, void* stream);
+                             int32_t out_dim, float* out, float* rowsum, const pit_tail_plan_t* plan, void* stream);
 int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
                               const float* period, const float* y, const float* scale,
                               const pit_rowstat_t* stat, const float* b1, const float* w2, const float* b2,
                               int32_t out_dim, const float* rowsum, const float* d_out, float* d_y,
-                              float* d_scale, float* d_b1, float* d_w2, float* d_b2, void* stream);
+                              float* d_scale, float* d_b1, float* d_w2, float* d_b2, const pit_tail_plan_t* plan,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,12 +13,13 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTS = (
     "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
     "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward",
     "pit_decoder_tail_supported", "pit_decoder_tail_forward", "pit_decoder_tail_backward",
+    "pit_tail_plan_workspace_bytes", "pit_tail_plan_rows", "pit_tail_plan_fill",
     "pit_head_scale_forward", "pit_head_scale_backward",
     "pit_bias_act_supported", "pit_bias_act_forward", "pit_bias_act_backward",
     "pit_rel_lp_supported", "pit_rel_lp_forward", "pit_rel_lp_backward",
@@ -33,6 +34,11 @@ class Problem(C.Structure):
 class RowStat(C.Structure):
     _fields_ = [("v_min", C.c_void_p), ("v_lo", C.c_void_p), ("v_hi", C.c_void_p),
                 ("weight", C.c_float), ("masked", C.c_int32)]
+
+
+class TailPlan(C.Structure):
+    _fields_ = [("rec", C.c_void_p), ("tile_off", C.c_void_p), ("tile_cnt", C.c_void_p), ("cand", C.c_void_p), ("d2", C.c_void_p),
+                ("n_tiles", C.c_int32)]
 
 
 def _load() -> C.CDLL:
@@ -55,9 +61,14 @@ def _load() -> C.CDLL:
                                         f32p, i64, i64, i32, f32p, f32p, p, C.c_size_t, p]
     lib.pit_decoder_tail_supported.argtypes = [C.POINTER(Problem), i32]
     lib.pit_decoder_tail_forward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
-                                             f32p, f32p, f32p, i32, f32p, f32p, p]
+                                             f32p, f32p, f32p, i32, f32p, f32p, C.POINTER(TailPlan), p]
     lib.pit_decoder_tail_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
-                                              f32p, f32p, f32p, i32, f32p, f32p, f32p, f32p, f32p, f32p, f32p, p]
+                                              f32p, f32p, f32p, i32, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                                              C.POINTER(TailPlan), p]
+    lib.pit_tail_plan_workspace_bytes.argtypes = [C.POINTER(Problem)]
+    lib.pit_tail_plan_workspace_bytes.restype = C.c_size_t
+    lib.pit_tail_plan_rows.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, C.POINTER(RowStat), p, p, p, C.c_size_t, p]
+    lib.pit_tail_plan_fill.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, C.POINTER(RowStat), p, p, p, p, p, C.c_size_t, p]
     lib.pit_head_scale_forward.argtypes = [f32p, f32p, i32, p]
     lib.pit_head_scale_backward.argtypes = [f32p, f32p, f32p, f32p, i32, p]
     lib.pit_bias_act_supported.argtypes = [i64, i32]

@@ -6,6 +6,7 @@
 
 #include "decoder_tail.cuh"
 #include "decoder_tail_mma.cuh"
+#include "decoder_tail_plan.cuh"
 #include "dense_attention.cuh"
 #include "local_attention.cuh"
 #include "mlp_epilogue.cuh"
@@ -46,6 +47,12 @@ cudaError_t tail_backward(int geo, const TallPlan& plan, const TailParams& P, cu
 // tu_tail_mma_fwd.cu / tu_tail_mma_bwd.cu  (plan.rows_per_unit counts 16-row tiles per CTA)
 cudaError_t tail_mma_forward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
 cudaError_t tail_mma_backward(int geo, const TallPlan& plan, const TailParams& P, cudaStream_t st);
+// tu_tail_plan_build.cu / tu_tail_plan_fwd.cu / tu_tail_plan_bwd.cu  (plan.rows_per_unit is unused: the tile plan carries tiles_per_cta)
+size_t tail_plan_workspace_bytes(int N);
+cudaError_t tail_plan_rows(int geo, int cpl, PlanBuildParams B, int32_t* tile_off, int32_t* tile_cnt, void* ws, cudaStream_t st);
+cudaError_t tail_plan_fill(int geo, int cpl, PlanBuildParams B, void* ws, cudaStream_t st);
+cudaError_t tail_plan_forward(int geo, const TallPlan& plan, const TailParams& P, const TailPlanDev& V, cudaStream_t st);
+cudaError_t tail_plan_backward(int geo, const TallPlan& plan, const TailParams& P, const TailPlanDev& V, cudaStream_t st);
 // tu_wide.cu
 int wide_pad(int width);
 cudaError_t wide_forward(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);

@@ -460,6 +460,74 @@ TallPlan plan_tail_mma_bwd(const pit_problem_t* p, int out_dim) {
   return c;
 }
 
+// Tile-plan variant (decoder_tail_plan.cuh): needs a plan from pit_tail_plan_*; hidden width 32 or 64.
+bool tail_plan_eligible(const pit_problem_t* p, int out_dim, const pit_tail_plan_t* plan) {
+  const int c = p->dim;
+  return plan && plan->rec && plan->tile_off && plan->tile_cnt && plan->cand && plan->d2 && plan->n_tiles == (p->n_out + pit::TP_ROWS - 1) / pit::TP_ROWS &&
+         tail_mma_enabled() && tail_eligible(p, out_dim) && (c == 32 || c == 64);
+}
+
+pit::TailPlanDev tail_plan_view(const pit_tail_plan_t* plan, int tiles_per_cta, int round) {
+  pit::TailPlanDev V{};
+  V.rec = static_cast<const float4*>(plan->rec);
+  V.tile_off = plan->tile_off;
+  V.tile_cnt = plan->tile_cnt;
+  V.cand = plan->cand;
+  V.d2 = plan->d2;
+  V.n_tiles = plan->n_tiles;
+  V.tiles_per_cta = tiles_per_cta;
+  V.round = round;
+  return V;
+}
+
+// One warp per sample (at most 8 warps); equal tile shares for `ctas_per_sm` resident CTAs per SM.
+void plan_tail_plan_grid(const pit_problem_t* p, const pit_tail_plan_t* plan, TallPlan& c, int ctas_per_sm, int round) {
+  const int warps = p->batch < pit::TP_MAX_WARPS ? p->batch : pit::TP_MAX_WARPS;
+  c.threads = 32 * warps;
+  const int target = sm_count() * ctas_per_sm;
+  (void)round;  // equal shares matter more than whole rounds: a partly filled last round only idles the preparing warps
+  const int per_cta = (plan->n_tiles + target - 1) / target;
+  c.rows_per_unit = per_cta;
+  c.grid = (plan->n_tiles + per_cta - 1) / per_cta;
+}
+
+TallPlan plan_tail_plan_fwd(const pit_problem_t* p, int out_dim, const pit_tail_plan_t* plan) {
+  TallPlan c{};
+  if (!tail_plan_eligible(p, out_dim, plan)) return c;
+  const int warps = p->batch < pit::TP_MAX_WARPS ? p->batch : pit::TP_MAX_WARPS;
+  c.l4 = warps < 4 ? warps : 4;  // tiles per round (kept in l4): 4 keeps three CTAs per SM at ~37 KB each and leaves most of the 228 KB to L1
+  plan_tail_plan_grid(p, plan, c, 3, c.l4);
+  c.smem = pit::tp_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim, c.l4);
+  if (c.smem > (size_t)max_smem_optin() - 1024) return c;
+  c.ok = true;
+  return c;
+}
+
+TallPlan plan_tail_plan_bwd(const pit_problem_t* p, int out_dim, const pit_tail_plan_t* plan) {
+  TallPlan c{};
+  if (!tail_plan_eligible(p, out_dim, plan)) return c;
+  plan_tail_plan_grid(p, plan, c, 2, pit::TP_BWD_ROUND);
+  const int W = p->batch * p->dim;
+  const size_t fixed = pit::tp_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, 0);
+  const size_t per_slot = (size_t)p->n_head * W * 4 + 4;
+  for (int per_sm = 2; per_sm >= 1; --per_sm) {
+    const size_t budget = ((size_t)max_smem_optin() + 1024) / per_sm - 2048;
+    if (budget <= fixed) continue;
+    int n = (int)((budget - fixed) / per_slot);
+    if (n > 32) n = 32;
+    if (n > p->n_in) n = p->n_in;
+    if (n >= 12 || n == p->n_in || per_sm == 1) {
+      c.n_slots = n;
+      break;
+    }
+  }
+  if (c.n_slots < 1) return c;
+  c.smem = pit::tp_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, c.n_slots);
+  if (c.smem > (size_t)max_smem_optin() - 1024) return c;
+  c.ok = true;
+  return c;
+}
+
 pit::TailParams tail_params(const pit_problem_t* p, const TallPlan& c, const float* mesh_out, const float* mesh_in,
                             const float* period, const float* y, const float* scale, const pit_rowstat_t* st,
                             const float* b1, const float* w2, const float* b2, int out_dim) {
@@ -890,6 +958,68 @@ int pit_bias_act_backward(const float* z, const float* bias, const float* d_out,
   return PIT_OK;
 }
 
+namespace {
+int check_tail_plan_args(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                         const pit_rowstat_t* stat, void* workspace, size_t workspace_bytes) {
+  if (int rc = check_problem(p)) return rc;
+  if (!mesh_out || !mesh_in || !workspace) return fail(PIT_ERR_ARG, "null pointer");
+  if (int rc = check_stat(p, stat, period)) return rc;
+  if (p->mesh_batched || p->n_in > pit::TALL_MAX_M) return fail(PIT_ERR_ARG, "tail plan: needs shared meshes with M <= %d", pit::TALL_MAX_M);
+  const size_t need = launch::tail_plan_workspace_bytes(p->n_out);
+  if (workspace_bytes < need) return fail(PIT_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
+  return PIT_OK;
+}
+
+pit::PlanBuildParams plan_build_params(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                                       const pit_rowstat_t* stat) {
+  pit::PlanBuildParams B{};
+  B.mesh_out = mesh_out;
+  B.mesh_in = mesh_in;
+  B.period = p->variant == PIT_EUCLID ? nullptr : period;
+  B.v_min = stat->v_min;
+  B.v_lo = stat->v_lo;
+  B.v_hi = stat->v_hi;
+  B.masked = stat->masked;
+  B.N = p->n_out;
+  B.M = p->n_in;
+  B.sd = p->space_dim;
+  B.n_tiles = (p->n_out + pit::TP_ROWS - 1) / pit::TP_ROWS;
+  return B;
+}
+}  // namespace
+
+size_t pit_tail_plan_workspace_bytes(const pit_problem_t* p) {
+  if (check_problem(p) != PIT_OK) return 0;
+  return launch::tail_plan_workspace_bytes(p->n_out);
+}
+
+int pit_tail_plan_rows(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                       const pit_rowstat_t* stat, int32_t* tile_off, int32_t* tile_cnt, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (int rc = check_tail_plan_args(p, mesh_out, mesh_in, period, stat, workspace, workspace_bytes)) return rc;
+  if (!tile_off || !tile_cnt) return fail(PIT_ERR_ARG, "null pointer");
+  PIT_CUDA(launch::tail_plan_rows(geo_of(p), cpl_of(p->n_in), plan_build_params(p, mesh_out, mesh_in, period, stat), tile_off, tile_cnt, workspace,
+                                  static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
+int pit_tail_plan_fill(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                       const pit_rowstat_t* stat, const int32_t* tile_off, void* rec, int16_t* cand, float* d2,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_tail_plan_args(p, mesh_out, mesh_in, period, stat, workspace, workspace_bytes)) return rc;
+  if (!tile_off || !rec || !cand || !d2) return fail(PIT_ERR_ARG, "null pointer");
+  if (!aligned16(rec)) return fail(PIT_ERR_ARG, "tail plan: rec must be 16-byte aligned");
+  pit::PlanBuildParams B = plan_build_params(p, mesh_out, mesh_in, period, stat);
+  B.tile_off = tile_off;
+  B.rec = static_cast<float4*>(rec);
+  B.cand = cand;
+  B.d2 = d2;
+  PIT_CUDA(launch::tail_plan_fill(geo_of(p), cpl_of(p->n_in), B, workspace, static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
 int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim) {
   if (check_problem(p) != PIT_OK) return 0;
   if (!tail_eligible(p, out_dim)) return 0;
@@ -898,16 +1028,26 @@ int pit_decoder_tail_supported(const pit_problem_t* p, int32_t out_dim) {
 
 int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
                              const float* y, const float* scale, const pit_rowstat_t* stat, const float* b1, const float* w2,
-                             const float* b2, int32_t out_dim, float* out, float* rowsum, void* stream) {
+                             const float* b2, int32_t out_dim, float* out, float* rowsum, const pit_tail_plan_t* tile_plan,
+                             void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (!mesh_out || !mesh_in || !y || !scale || !b1 || !w2 || !b2 || !out || !rowsum) return fail(PIT_ERR_ARG, "null pointer");
   if (int rc = check_stat(p, stat, period)) return rc;
   if (!tail_eligible(p, out_dim)) return fail(PIT_ERR_ARG, "decoder tail: unsupported configuration (see pit_decoder_tail_supported)");
   if (!aligned16(y) || !aligned16(b1) || !aligned16(w2)) return fail(PIT_ERR_ARG, "decoder tail: y, b1, w2 must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TallPlan tiled = plan_tail_plan_fwd(p, out_dim, tile_plan);
+  if (tiled.ok) {
+    pit::TailParams P = tail_params(p, tiled, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
+    P.out = out;
+    P.rowsum = rowsum;
+    PIT_CUDA(launch::tail_plan_forward(geo_of(p), tiled, P, tail_plan_view(tile_plan, tiled.rows_per_unit, tiled.l4), st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PIT_OK;
+  }
   const TallPlan mma = plan_tail_mma_fwd(p, out_dim);
   const TallPlan plan = mma.ok ? mma : plan_tail_fwd(p);
   if (!plan.ok) return fail(PIT_ERR_ARG, "decoder tail: no launch plan");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
   P.out = out;
   P.rowsum = rowsum;
@@ -922,7 +1062,8 @@ int pit_decoder_tail_forward(const pit_problem_t* p, const float* mesh_out, cons
 int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
                               const float* y, const float* scale, const pit_rowstat_t* stat, const float* b1, const float* w2,
                               const float* b2, int32_t out_dim, const float* rowsum, const float* d_out, float* d_y,
-                              float* d_scale, float* d_b1, float* d_w2, float* d_b2, void* stream) {
+                              float* d_scale, float* d_b1, float* d_w2, float* d_b2, const pit_tail_plan_t* tile_plan,
+                              void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (!mesh_out || !mesh_in || !y || !scale || !b1 || !w2 || !b2 || !rowsum || !d_out || !d_y || !d_scale || !d_b1 || !d_w2 || !d_b2)
     return fail(PIT_ERR_ARG, "null pointer");
@@ -930,8 +1071,9 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   if (!tail_eligible(p, out_dim)) return fail(PIT_ERR_ARG, "decoder tail: unsupported configuration (see pit_decoder_tail_supported)");
   if (!aligned16(y) || !aligned16(b1) || !aligned16(w2) || !aligned16(d_y) || !aligned16(d_b1) || !aligned16(d_w2))
     return fail(PIT_ERR_ARG, "decoder tail: y, b1, w2 and their gradients must be 16-byte aligned");
-  const TallPlan mma = plan_tail_mma_bwd(p, out_dim);
-  const TallPlan plan = mma.ok ? mma : plan_tail_bwd(p, out_dim);
+  const TallPlan tiled = plan_tail_plan_bwd(p, out_dim, tile_plan);
+  const TallPlan mma = tiled.ok ? TallPlan{} : plan_tail_mma_bwd(p, out_dim);
+  const TallPlan plan = tiled.ok ? tiled : (mma.ok ? mma : plan_tail_bwd(p, out_dim));
   if (!plan.ok) return fail(PIT_ERR_ARG, "decoder tail: no launch plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   pit::TailParams P = tail_params(p, plan, mesh_out, mesh_in, period, y, scale, stat, b1, w2, b2, out_dim);
@@ -948,7 +1090,9 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   PIT_CUDA(cudaMemsetAsync(d_b1, 0, c * sizeof(float), st));
   PIT_CUDA(cudaMemsetAsync(d_w2, 0, (size_t)out_dim * c * sizeof(float), st));
   PIT_CUDA(cudaMemsetAsync(d_b2, 0, (size_t)out_dim * sizeof(float), st));
-  if (mma.ok)
+  if (tiled.ok)
+    PIT_CUDA(launch::tail_plan_backward(geo_of(p), plan, P, tail_plan_view(tile_plan, plan.rows_per_unit, pit::TP_BWD_ROUND), st));
+  else if (mma.ok)
     PIT_CUDA(launch::tail_mma_backward(geo_of(p), plan, P, st));
   else
     PIT_CUDA(launch::tail_backward(geo_of(p), plan, P, st));

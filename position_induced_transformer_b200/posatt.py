@@ -136,21 +136,36 @@ class _timed:
         return False
 
 
-class _MeshCache:
-    """Per-mesh-pair constants of shared meshes, reused across steps.
+class _MeshEntry:
+    """What the cache keeps for one pair of shared meshes: contiguous copies, wrap period, row statistics and -- built on
+    first use by a decoder -- the tile plan of the fused decoder tail."""
 
-    For a pair of shared meshes the contiguous copies, the wrap period and the order statistics
-    v_min / v_lo / v_hi depend on the meshes and the locality only -- not on lmda -- and the scripts
-    pass the same mesh tensors at every step (train_darcy.py:88-96, 128; note that they are column-major
-    views of a transposed numpy array, so even `.contiguous()` is a copy), while the reference re-sorts
-    every row each time (pit.py:136).  An entry is keyed by the storage address, offset, shape, strides
-    and autograd version of both incoming tensors and keeps a strong reference to them, so the address
-    cannot be recycled while the entry lives and any in-place write (which bumps the version) misses.
-    Per-sample meshes (posatt / posatt_cross) change every batch; their entries serve the repeated uses inside
-    one step (processor blocks, backward) and are evicted in insertion order.
+    __slots__ = ("mesh_out", "mesh_in", "period", "stats", "tail_plan", "keep_alive")
+
+    def __init__(self, mesh_out, mesh_in, period, stats, keep_alive):
+        self.mesh_out, self.mesh_in, self.period, self.stats = mesh_out, mesh_in, period, stats
+        self.tail_plan = None
+        self.keep_alive = keep_alive
+
+
+class _MeshCache:
+    """Per-mesh-pair constants of SHARED meshes, reused across steps.
+
+    For a pair of shared meshes the contiguous copies, the wrap period, the order statistics v_min / v_lo / v_hi and the
+    decoder's tile plan depend on the meshes and the locality only -- not on lmda -- and the scripts pass the same mesh
+    tensors at every step (train_darcy.py:88-96, 128; note that they are column-major views of a transposed numpy array,
+    so even `.contiguous()` is a copy), while the reference re-sorts every row each time (pit.py:136).
+
+    An entry is keyed by the storage address, shape, strides and autograd version counter of both incoming tensors and
+    keeps a strong reference to them, so the address cannot be recycled while the entry lives and any in-place write
+    through torch (which bumps the version) misses.  CAVEAT: writes that do NOT bump the version counter -- `mesh.data.copy_`,
+    a CUDA-graph replay that fills a static mesh buffer, an external kernel, NCCL -- are invisible here; code that rewrites
+    a shared mesh that way must call `mesh_cache.clear()` (or set `mesh_cache.enabled = False`).  Tensors without a version
+    counter (created under `torch.inference_mode()`) and per-sample meshes (B, L, sd), which change with every batch, are
+    never cached: their statistics are recomputed by every call.  Least recently used entries are evicted first.
     """
 
-    def __init__(self, capacity: int = 32):
+    def __init__(self, capacity: int = 16):
         self.capacity = capacity
         self.entries = {}
         self.hits = self.misses = 0
@@ -158,10 +173,15 @@ class _MeshCache:
 
     @staticmethod
     def _sig(t: torch.Tensor):
-        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version, t.device.index)
+        try:
+            version = t._version
+        except RuntimeError:          # inference tensors do not track a version counter
+            return None
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), version, t.device.index)
 
     def key(self, mesh_out, mesh_in, variant, locality):
-        return (self._sig(mesh_out), self._sig(mesh_in), variant, float(locality))
+        a, b = self._sig(mesh_out), self._sig(mesh_in)
+        return None if a is None or b is None else (a, b, variant, float(locality))
 
     def get(self, key):
         hit = self.entries.get(key)
@@ -169,12 +189,13 @@ class _MeshCache:
             self.misses += 1
             return None
         self.hits += 1
-        return hit[0]
+        self.entries[key] = self.entries.pop(key)      # most recently used last
+        return hit
 
-    def put(self, key, value, keep_alive):
-        if len(self.entries) >= self.capacity:
+    def put(self, key, entry):
+        while len(self.entries) >= self.capacity:
             self.entries.pop(next(iter(self.entries)))
-        self.entries[key] = (value, keep_alive)
+        self.entries[key] = entry
 
     def clear(self):
         self.entries.clear()
@@ -200,6 +221,7 @@ def _zeros(shape, device) -> torch.Tensor:
 
 def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
     """(v_min, v_lo, v_hi, w, masked): order statistics replacing torch.quantile's row sort (uncached)."""
+    _require(0.0 <= locality <= 1.0, f"quantile() q values must be in the range [0, 1], got locality={locality}")
     masked = locality < 1.0
     k_lo, k_hi, w = _cabi.quantile_ranks(locality, st.M) if masked else (0, 0, 0.0)
     if not masked and mesh_out.data_ptr() == mesh_in.data_ptr() and mesh_out.shape == mesh_in.shape:
@@ -214,28 +236,90 @@ def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
     return stats[0], stats[1], stats[2], w, masked
 
 
+def _meshes_are_constants(mesh_out, mesh_in) -> None:
+    # dist2att is differentiable w.r.t. the coordinates in the reference; no call site uses that and the
+    # fused kernels do not produce dX -- refuse loudly instead of returning a silent zero gradient
+    if torch.is_grad_enabled() and (mesh_out.requires_grad or mesh_in.requires_grad):
+        raise RuntimeError("position-attention: gradients w.r.t. mesh coordinates are not implemented (meshes must not require grad)")
+
+
 def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, locality: float):
-    """Contiguous meshes, the validated stage, the wrap period and the row statistics -- cached for shared meshes."""
-    # Shared meshes hit across steps; per-sample meshes hit within a step (the four processor blocks and the
-    # backward see the same tensors).  The strong reference held by an entry keeps the address from being recycled.
+    """(mesh_out, mesh_in, stage, period, stats, entry): contiguous meshes, the validated stage, the wrap period and the
+    row statistics; `entry` is the cache entry for shared meshes (None when nothing is cached)."""
+    _meshes_are_constants(mesh_out, mesh_in)
     capturing = mesh_in.is_cuda and torch.cuda.is_current_stream_capturing()
-    # inside a CUDA-graph capture per-sample meshes are graph inputs whose contents change between replays:
-    # their statistics must be recomputed by captured kernels, never taken from the cache
-    cacheable = mesh_cache.enabled and mesh_in.is_cuda and not (capturing and mesh_in.dim() == 3)
+    cacheable = mesh_cache.enabled and mesh_in.is_cuda and mesh_in.dim() == 2
     key = mesh_cache.key(mesh_out, mesh_in, variant, locality) if cacheable else None
-    hit = mesh_cache.get(key) if cacheable else None
+    hit = mesh_cache.get(key) if key is not None else None
     if hit is not None:
-        mo, mi, period, stats = hit
-        return mo, mi, _Stage(mo, mi, values, n_head, variant), period, stats
+        return hit.mesh_out, hit.mesh_in, _Stage(hit.mesh_out, hit.mesh_in, values, n_head, variant), hit.period, hit.stats, hit
     mo, mi = mesh_out.contiguous(), mesh_in.contiguous()
     st = _Stage(mo, mi, values, n_head, variant)
     with torch.cuda.device(st.device):
         period = wrap_period(mi, variant)
         stats = row_statistics(st, mo, mi, period, float(locality))
+    entry = None
     # entries created while a CUDA graph is being captured would point into the graph's private pool: do not keep them
-    if cacheable and not capturing:
-        mesh_cache.put(key, (mo, mi, period, stats), (mesh_out, mesh_in))
-    return mo, mi, st, period, stats
+    if key is not None and not capturing:
+        entry = _MeshEntry(mo, mi, period, stats, (mesh_out, mesh_in))
+        mesh_cache.put(key, entry)
+    return mo, mi, st, period, stats, entry
+
+
+class TailPlan:
+    """Tile plan of a decoder stage (include/pit_posatt.h, pit_tail_plan_t): rows sorted by candidate set, 32 per tile."""
+
+    def __init__(self, rec, tile_off, tile_cnt, cand, d2):
+        self.rec, self.tile_off, self.tile_cnt, self.cand, self.d2 = rec, tile_off, tile_cnt, cand, d2
+        self.n_tiles = tile_cnt.numel()
+        self.n_cand = cand.numel()          # candidate entries including the padding of every list to a multiple of 8
+        self.struct = _cabi.TailPlan(rec.data_ptr(), tile_off.data_ptr(), tile_cnt.data_ptr(), cand.data_ptr(), d2.data_ptr(), self.n_tiles)
+
+
+_TAIL_PLAN = True
+_TAIL_PLAN_MAX_MEAN = 16      # candidates per tile (mean) above which the plan is not used
+
+
+def use_tail_plan(enabled: bool) -> None:
+    """Switch the cached tile plan of the fused decoder tail on or off (off: the kernels scan the latent mesh per launch)."""
+    global _TAIL_PLAN
+    _TAIL_PLAN = bool(enabled)
+
+
+def build_tail_plan(st: _Stage, mesh_out, mesh_in, period, stats) -> TailPlan:
+    """Runs the two construction stages of the C ABI; one 4-byte device->host read in between sizes the candidate array."""
+    v_min, v_lo, v_hi, w, masked = stats
+    rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
+    dev = st.device
+    with torch.cuda.device(dev):
+        n_tiles = (st.N + 31) // 32
+        ws_bytes = int(_cabi.lib.pit_tail_plan_workspace_bytes(C.byref(st.problem)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        tile_off = torch.empty(n_tiles + 1, dtype=torch.int32, device=dev)
+        tile_cnt = torch.empty(n_tiles, dtype=torch.int32, device=dev)
+        _cabi.check(_cabi.lib.pit_tail_plan_rows(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), C.byref(rs),
+                                                 tile_off.data_ptr(), tile_cnt.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev)),
+                    "pit_tail_plan_rows")
+        total = int(tile_off[-1].item())
+        rec = torch.empty((n_tiles * 32, 4), dtype=torch.float32, device=dev)
+        cand = torch.empty(max(total, 1), dtype=torch.int16, device=dev)
+        d2 = torch.empty((max(total, 1), 32), dtype=torch.float32, device=dev)
+        _cabi.check(_cabi.lib.pit_tail_plan_fill(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), C.byref(rs),
+                                                 tile_off.data_ptr(), rec.data_ptr(), cand.data_ptr(), d2.data_ptr(), ws.data_ptr(),
+                                                 ws_bytes, _stream(dev)), "pit_tail_plan_fill")
+    return TailPlan(rec, tile_off, tile_cnt, cand, d2)
+
+
+def tail_plan_for(entry: Optional[_MeshEntry], st: _Stage, hidden: int) -> Optional[TailPlan]:
+    """The cached plan of a shared-mesh decoder stage, built on first use (never while a CUDA graph is being captured)."""
+    if not _TAIL_PLAN or entry is None or st.batched or st.M > 1024 or hidden not in (32, 64):
+        return None
+    if entry.tail_plan is None and not torch.cuda.is_current_stream_capturing():
+        plan = build_tail_plan(st, entry.mesh_out, entry.mesh_in, entry.period, entry.stats)
+        # small or incoherent meshes do not pack (a 43 x 43 grid has more distinct candidate sets than 32-row tiles): with more
+        # than one 16-candidate block per tile on average the per-launch scan of the latent mesh is the better kernel
+        entry.tail_plan = plan if plan.n_cand <= _TAIL_PLAN_MAX_MEAN * plan.n_tiles else False
+    return entry.tail_plan or None
 
 
 def _rowstat_struct(v_min, v_lo, v_hi, w: float, masked: bool) -> _cabi.RowStat:
@@ -250,7 +334,7 @@ class _PositionAttention(torch.autograd.Function):
         _require(values.is_cuda, f"values must be a CUDA tensor (position-attention has no CPU path), got {values.device}")
         scale_shape = scale.shape
         scale = scale.reshape(-1).contiguous()
-        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked) = prepare_meshes(
+        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked), _entry = prepare_meshes(
             mesh_out, mesh_in, values, n_head, variant, float(locality))
         _check_tensor("scale", scale, st.device)
         _require(scale.numel() == st.H, f"scale must have n_head={st.H} entries, got {scale.numel()}")
@@ -456,27 +540,31 @@ class _DecoderTail(torch.autograd.Function):
         b1, w2, b2 = b1.contiguous(), w2.contiguous(), b2.contiguous()
         out_dim = w2.shape[0]
         # the stage descriptor treats the hidden width as the value width
-        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked) = prepare_meshes(
+        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked), entry = prepare_meshes(
             mesh_out, mesh_in, y.reshape(B, M, H * Cw)[:, :, :Cw], H, variant, float(locality))
         st.problem.dim = Cw
+        plan = tail_plan_for(entry, st, Cw)
         with torch.cuda.device(st.device):
             out = torch.empty((B, st.N, out_dim), dtype=torch.float32, device=st.device)
-            rowsum = torch.empty((H, st.N), dtype=torch.float32, device=st.device)
+            # opaque to the caller: row sums (and, with a tile plan, sum_j P^ d2 per row in tile order), consumed by the backward
+            rowsum = torch.empty((2 * H, (st.N + 31) // 32 * 32), dtype=torch.float32, device=st.device)
             rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
             with _timed("tail_fwd", st, False):
                 _cabi.check(_cabi.lib.pit_decoder_tail_forward(
                     C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), y.data_ptr(), scale.data_ptr(),
                     C.byref(rs), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out_dim, out.data_ptr(), rowsum.data_ptr(),
-                    _stream(st.device)), "pit_decoder_tail_forward")
+                    C.byref(plan.struct) if plan is not None else None, _stream(st.device)), "pit_decoder_tail_forward")
         ctx.save_for_backward(y, scale, b1, w2, b2, mesh_out, mesh_in, period if period is not None else scale.new_empty(0),
                               v_min, v_lo, v_hi, rowsum)
         ctx.meta = (variant, w, masked, scale_shape, out_dim)
+        ctx.plan = plan          # keeps the plan's tensors alive until the backward has run
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         y, scale, b1, w2, b2, mesh_out, mesh_in, period, v_min, v_lo, v_hi, rowsum = ctx.saved_tensors
         variant, w, masked, scale_shape, out_dim = ctx.meta
+        plan = ctx.plan
         period = period if period.numel() else None
         B, M, H, Cw = y.shape
         st = _Stage(mesh_out, mesh_in, y.reshape(B, M, H * Cw)[:, :, :Cw], H, variant)
@@ -491,8 +579,8 @@ class _DecoderTail(torch.autograd.Function):
                 _cabi.check(_cabi.lib.pit_decoder_tail_backward(
                     C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), y.data_ptr(), scale.data_ptr(),
                     C.byref(rs), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out_dim, rowsum.data_ptr(), d_out.data_ptr(),
-                    d_y.data_ptr(), d_scale.data_ptr(), d_b1.data_ptr(), d_w2.data_ptr(), d_b2.data_ptr(), _stream(st.device)),
-                    "pit_decoder_tail_backward")
+                    d_y.data_ptr(), d_scale.data_ptr(), d_b1.data_ptr(), d_w2.data_ptr(), d_b2.data_ptr(),
+                    C.byref(plan.struct) if plan is not None else None, _stream(st.device)), "pit_decoder_tail_backward")
         return d_y, d_scale.reshape(scale_shape), d_b1, d_w2, d_b2, None, None, None, None
 
 

@@ -45,9 +45,13 @@ def _case(variant, sd, N, M, B, D, H, Cw, O, q, seed):
     ("euclid", 2, 5, 6, 2, 8, 1, 32, 1, 0.5),            # tensor-core tail at its smallest: one tile, one chunk, six columns
     ("euclid", 2, 1000, 9, 1, 4, 2, 64, 1, 0.3),         # one sample, nine latent points
 ])
-def test_decoder_tail_matches_oracle(variant, sd, N, M, B, D, H, Cw, O, q, cuda_device, host_scale_map):
+@pytest.mark.parametrize("tile_plan", [True, False])   # cached tile plan (hidden width 32 / 64) or a latent-mesh scan per launch
+def test_decoder_tail_matches_oracle(variant, sd, N, M, B, D, H, Cw, O, q, tile_plan, cuda_device, host_scale_map, request):
     import position_induced_transformer_b200.pit as pit_mod
+    from position_induced_transformer_b200 import posatt as posatt_mod
     from position_induced_transformer_b200.posatt import decoder_tail, decoder_tail_supported
+    posatt_mod.use_tail_plan(tile_plan)
+    request.addfinalizer(lambda: posatt_mod.use_tail_plan(True))
     mesh_out, mesh_in, feats, p, g = _case(variant, sd, N, M, B, D, H, Cw, O, q, seed=N + M + Cw)
     # oracle
     pc = {k: v.clone().requires_grad_(True) for k, v in p.items()}
@@ -75,6 +79,72 @@ def test_decoder_tail_matches_oracle(variant, sd, N, M, B, D, H, Cw, O, q, cuda_
         assert rel_linf(pg[k].grad.cpu(), pc[k].grad, floor=1e-6) <= 1e-4, k
 
 
+def _grid(n):
+    import numpy as np
+    ax = np.linspace(0, 1, n)
+    return torch.tensor(np.vstack([g.ravel() for g in np.meshgrid(ax, ax)]).T, dtype=torch.float)
+
+
+@pytest.mark.parametrize("case", ["darcy130", "random", "unmasked", "periodic1d"])
+def test_tail_plan_structure(case, cuda_device):
+    """The plan is a permutation of the rows cut into 32-row tiles whose candidate lists are sorted, duplicate-free and
+    contain every column any head can keep (checked against the oracle's kept mask for several lmda)."""
+    from position_induced_transformer_b200 import posatt as pa
+    g = torch.Generator().manual_seed(5)
+    variant, q = "euclid", 0.02
+    if case == "darcy130":
+        mesh_out, mesh_in = _grid(130), _grid(16)
+    elif case == "random":
+        mesh_out, mesh_in = torch.rand(1000, 2, generator=g), torch.rand(300, 2, generator=g)
+    elif case == "unmasked":
+        mesh_out, mesh_in, q = torch.rand(70, 2, generator=g), torch.rand(40, 2, generator=g), 1.0
+    else:
+        variant, q = "periodic1d", 0.05
+        mesh_out, mesh_in = torch.linspace(0, 1, 513)[:-1].reshape(-1, 1), torch.linspace(0, 1, 129)[:-1].reshape(-1, 1)
+    N, M = mesh_out.shape[0], mesh_in.shape[0]
+    dev = cuda_device
+    values = torch.zeros(2, M, 64, device=dev)
+    mo, mi, st, period, stats, _ = pa.prepare_meshes(mesh_out.to(dev), mesh_in.to(dev), values, 2, variant, q)
+    plan = pa.build_tail_plan(st, mo, mi, period, stats)
+    torch.cuda.synchronize()
+    n_tiles = (N + 31) // 32
+    assert plan.n_tiles == n_tiles
+    rows = plan.rec[:, 3].contiguous().view(torch.int32).cpu()
+    assert sorted(rows[rows >= 0].tolist()) == list(range(N)) and int((rows < 0).sum()) == n_tiles * 32 - N
+    off = plan.tile_off.cpu().tolist()
+    cnt = plan.tile_cnt.cpu().tolist()
+    cand = plan.cand.cpu().tolist()
+    assert off[0] == 0 and all(b - a == (n + 7) // 8 * 8 for a, b, n in zip(off, off[1:], cnt))
+    # records carry the row's statistics, the distance matrix the reference's squared distances bit for bit
+    rec = plan.rec.cpu()
+    valid = rows >= 0
+    for i in range(3 if q < 1.0 else 1):
+        assert torch.equal(rec[valid][:, i], stats[i].cpu()[rows[valid].long()])
+    d2_ref = po.sqdist(mesh_out, mesh_in, variant)
+    d2_plan = plan.d2.cpu()
+    # superset of the kept sets
+    keep_any = torch.zeros(N, M, dtype=torch.bool)
+    for lm in (-1.3, 0.0, 0.4, 1.1, 2.5):
+        scale = po.head_scale(torch.full((1, 1, 1), lm))
+        _, _, keep = po.exact_weights(mesh_out, mesh_in, scale, q, variant)
+        keep_any |= keep[0]
+    sizes = []
+    for t in range(n_tiles):
+        c = cand[off[t]:off[t] + cnt[t]]
+        assert c == sorted(set(c)) and all(0 <= j < M for j in c)
+        sizes.append(len(c))
+        tile_rows = rows[t * 32:(t + 1) * 32]
+        need = keep_any[tile_rows[tile_rows >= 0].long()].any(0).nonzero().flatten().tolist()
+        assert set(need) <= set(c), (t, need, c)
+        live = tile_rows >= 0
+        want = d2_ref[tile_rows[live].long()][:, torch.tensor(c, dtype=torch.long)].T
+        assert torch.equal(d2_plan[off[t]:off[t] + cnt[t]][:, live], want), t
+    if case == "darcy130":     # sorted rows share their candidate set: most tiles fit one k-step of 8, nearly all one block of 16
+        assert sum(s <= 16 for s in sizes) >= 0.9 * n_tiles
+    if case == "unmasked":
+        assert all(s == M for s in sizes)
+
+
 def test_pit_decoder_uses_the_fused_tail(cuda_device, host_scale_map):
     """pit.decoder takes the fused path for the stock layers and equals the two-module composition."""
     import position_induced_transformer_b200.pit as pit_mod
@@ -95,5 +165,5 @@ def test_pit_decoder_uses_the_fused_tail(cuda_device, host_scale_map):
         pit_mod.use_fused_decoder_tail(True)
     finally:
         torch.set_float32_matmul_precision(prev)
-    assert 1 <= fused_launches <= 3          # scale map + tail kernel (+ the row statistics if this mesh pair was not cached yet)
+    assert 1 <= fused_launches <= 6          # scale map + tail kernel (+ row statistics and the three plan-construction launches if this mesh pair was not cached yet)
     assert rel_linf(fused, plain) <= 1e-5

@@ -1,4 +1,5 @@
 """Host-side logic that needs no GPU: the CPU branches of the drop-in module equal the reference expressions."""
+import pytest
 import torch
 
 import position_induced_transformer_b200.pit as pit_mod
@@ -39,3 +40,33 @@ def test_head_scale_cpu_branch_is_the_reference_expression():
     from math import pi
     lmda = torch.rand(3, 1, 1, generator=torch.Generator().manual_seed(2))
     assert torch.equal(pit_mod.head_scale(lmda), torch.tan(0.25 * pi * (1 - 1e-7) * (1.0 + torch.sin(lmda))))   # pit.py:48
+
+
+def test_mesh_cache_skips_tensors_without_version_counter():
+    """Inference tensors have no version counter: they must bypass the cache instead of raising."""
+    from position_induced_transformer_b200.posatt import _MeshCache
+    cache = _MeshCache()
+    ok = torch.zeros(4, 2)
+    with torch.inference_mode():
+        inf = torch.zeros(4, 2)
+    assert cache.key(ok, ok, "euclid", 0.5) is not None
+    assert cache.key(inf, ok, "euclid", 0.5) is None and cache.key(ok, inf, "euclid", 0.5) is None
+
+
+def test_mesh_cache_is_lru():
+    from position_induced_transformer_b200.posatt import _MeshCache, _MeshEntry
+    cache = _MeshCache(capacity=2)
+    for k in ("a", "b"):
+        cache.put(k, _MeshEntry(None, None, None, None, None))
+    assert cache.get("a") is not None          # "a" becomes the most recently used
+    cache.put("c", _MeshEntry(None, None, None, None, None))
+    assert cache.get("b") is None and cache.get("a") is not None and cache.get("c") is not None
+
+
+def test_meshes_requiring_grad_are_refused():
+    from position_induced_transformer_b200.posatt import _meshes_are_constants
+    m = torch.zeros(4, 2, requires_grad=True)
+    with pytest.raises(RuntimeError, match="mesh coordinates"):
+        _meshes_are_constants(m, torch.zeros(4, 2))
+    with torch.no_grad():
+        _meshes_are_constants(m, m)
