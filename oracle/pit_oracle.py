@@ -77,3 +77,76 @@ def rel_lp_loss(true: torch.Tensor, pred: torch.Tensor, out_dim: int, p: int) ->
     q = pred.reshape(pred.shape[0], -1, out_dim)
     ratio = torch.norm(t - q, p=p, dim=1) / torch.norm(t, p=p, dim=1)
     return ratio.mean(-1).sum()
+
+
+# --------------------------------------------------------------------------------------
+# Workload-level helpers (driven by a `workload_specs.Spec`-like object; nothing here touches the CUDA library)
+# --------------------------------------------------------------------------------------
+
+def init_params(spec, seed: int = 0) -> Params:
+    """Random parameters with the reference's state_dict keys and shapes for a spec (Kaiming-normal Linear weights, lmda ~ U[0,1)
+    as pit.py:35; NOT the reference's RNG stream -- used where only shapes and magnitudes matter, e.g. CPU timing)."""
+    g = torch.Generator().manual_seed(seed)
+    sd, in_dim, out_dim, hid, heads, blocks, _, _ = spec.ctor
+    feat = in_dim if spec.family == "batched" else in_dim + sd      # shared-mesh scripts prepend the coordinates
+    p: Params = {}
+
+    def linear(name, fan_in, fan_out):
+        p[f"{name}.weight"] = torch.randn(fan_out, fan_in, generator=g) * (2.0 / fan_in) ** 0.5
+        p[f"{name}.bias"] = (torch.rand(fan_out, generator=g) * 2 - 1) / fan_in ** 0.5
+
+    def mlp(name, a, b, c):
+        linear(f"{name}.mlp1", a, b)
+        linear(f"{name}.mlp2", b, c)
+
+    p["down.lmda"] = torch.rand(heads, 1, 1, generator=g)
+    mlp("en_layer", spec.en_in if spec.en_in else heads * feat, hid, hid)
+    for i in range(blocks):
+        p[f"conv.{i}.lmda"] = torch.rand(heads, 1, 1, generator=g)
+        mlp(f"mlp.{i}", (1 + heads) * hid, hid, hid)
+    p["up.lmda"] = torch.rand(heads, 1, 1, generator=g)
+    mlp("de", heads * hid, hid, out_dim)
+    return p
+
+
+def _instance_norm(x: torch.Tensor) -> torch.Tensor:
+    """nn.InstanceNorm1d(hid) applied to (B, L, hid) through the permutes of train_vorticity.py:56, 59."""
+    return F.instance_norm(x.permute(0, 2, 1)).permute(0, 2, 1)
+
+
+def forward_spec(p: Params, spec, inputs):
+    """One model application for a spec: the `forward` its script defines."""
+    _, _, _, _, _, _, en_loc, de_loc = spec.ctor
+    if spec.family == "batched":
+        mesh_in, func_in, mesh_out = inputs
+        if spec.extra.get("latent") == "strided":        # train_naca.py:62-65
+            b = mesh_out.shape[0]
+            lead = mesh_out.shape[:-1]
+            ltt = mesh_out[:, ::spec.extra["x_down"], ::spec.extra["y_down"], :].reshape(b, -1, 2)
+            return forward_point_cloud(p, mesh_in, func_in, ltt, mesh_out.reshape(b, -1, 2), en_loc, de_loc).reshape(*lead, -1)
+        return forward_point_cloud(p, mesh_in, func_in, mesh_out, mesh_out, en_loc, de_loc)
+    mesh, ltt = spec.mesh, spec.mesh_ltt.reshape(-1, spec.mesh_ltt.shape[-1])
+    if spec.extra.get("instance_norm"):                  # train_vorticity.py:44-62
+        sd = ltt.shape[-1]
+        lead = mesh.shape[:-1]
+        m = mesh.reshape(-1, sd)
+        func_in = inputs[0].reshape(inputs[0].shape[0], m.shape[0], -1)
+        feats = torch.cat((m.unsqueeze(0).expand(func_in.shape[0], -1, -1), func_in), -1)
+        h = _instance_norm(encode(p, spec.variant, m, feats, ltt, en_loc))
+        h = _instance_norm(process(p, spec.variant, h, ltt, n_blocks_of(p)))
+        return decode(p, spec.variant, ltt, h, m, de_loc).reshape(func_in.shape[0], *lead, -1)
+    out = forward_shared_mesh(p, spec.variant, mesh, inputs[0], ltt, mesh, en_loc, de_loc)
+    return out + inputs[0] if spec.extra.get("residual") else out     # train_cylinder.py:52
+
+
+def step_loss(p: Params, spec, inputs, target) -> torch.Tensor:
+    """Training loss of one step, with the autoregressive rollout of train_vorticity.py:122-126 where the spec asks for it."""
+    out_dim, ord_ = spec.loss
+    if spec.rollout == 1:
+        return rel_lp_loss(target, forward_spec(p, spec, inputs), out_dim, ord_)
+    x, loss = inputs[0], 0.0
+    for t in range(spec.rollout):
+        out = forward_spec(p, spec, (x,))
+        loss = loss + rel_lp_loss(out, target[..., t:t + 1], out_dim, ord_)
+        x = torch.cat((x[..., 1:], out), -1)
+    return loss

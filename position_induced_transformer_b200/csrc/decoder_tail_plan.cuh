@@ -32,8 +32,10 @@ constexpr int TP_KB = 16;     // candidates per weight block held in shared memo
 constexpr int TP_MT = 2;      // m16 MMA tiles per warp pass
 constexpr int TP_CHUNK = 16 * TP_MT;  // hidden-vector columns per warp pass
 constexpr int TP_TPC = 2 * TP_MT;     // contiguous columns a thread owns inside a chunk (one float4)
-constexpr int TP_MAX_WARPS = 8;
-constexpr int TP_BWD_ROUND = 2;   // tiles prepared per round in the backward
+constexpr int TP_MAX_WARPS = 8;       // forward: one warp per sample
+constexpr int TP_BWD_MAX_WARPS = 16;  // backward: one warp per (sample, 32-column chunk), one CTA per SM
+constexpr int TP_BWD_ROUND = 4;   // tiles prepared per round in the backward
+constexpr int TP_FWD_CTAS = 2;    // resident forward CTAs per SM the register budget is set for (2: 128 registers, 3: 80)
 
 // Device view of a plan (all pointers into caller-owned buffers, see pit_tail_plan_t in include/pit_posatt.h).
 struct TailPlanDev {
@@ -214,40 +216,56 @@ __device__ __forceinline__ f32x2 dup2(float a) { return pk2(a, a); }
   {-0.49999993418f, 0.39893651669f, -0.24991680755f, 0.13251384598f, -0.06115497274f, 0.024314022073f, -0.007939450696f,       \
    0.0019746516026f, -0.0003397443039f, 3.5208560222e-05f, -1.6317331320e-06f}
 
-// u = -(Q(a)/2) exp(-x^2/2) = -erfc(|x|/sqrt 2)/2 for the two lanes of x; e = exp(-x^2/2); a = |x|.
-__device__ __forceinline__ f32x2 tpg_core(f32x2 x, f32x2& e, f32x2& a) {
+// u[i] = -(Q(a)/2) exp(-x^2/2) = -erfc(|x|/sqrt 2)/2 for the two lanes of each x[i]; e[i] = exp(-x^2/2); a[i] = |x|.
+// N independent Horner chains advance together (coefficient loop outermost), which is what hides the FFMA2 latency.
+template <int N>
+__device__ __forceinline__ void tpg_core(const f32x2 (&x)[N], f32x2 (&u)[N], f32x2 (&e)[N], f32x2 (&a)[N]) {
   constexpr float c[11] = TPG_COEFFS;
-  float x0, x1, g0, g1, e0, e1;
-  unpk2(x, x0, x1);
-  const f32x2 arg = mul2(mul2(x, x), dup2(-0.72134752044448170368f));  // -x^2 / 2 * log2(e)
-  unpk2(arg, g0, g1);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
-  e = pk2(e0, e1);
-  a = pk2(fabsf(x0), fabsf(x1));
-  f32x2 q = fma2(dup2(c[10]), a, dup2(c[9]));
 #pragma unroll
-  for (int k = 8; k >= 0; --k) q = fma2(q, a, dup2(c[k]));
-  return mul2(q, e);
+  for (int i = 0; i < N; ++i) {
+    float x0, x1, g0, g1, e0, e1;
+    unpk2(x[i], x0, x1);
+    const f32x2 arg = mul2(mul2(x[i], x[i]), dup2(-0.72134752044448170368f));  // -x^2 / 2 * log2(e)
+    unpk2(arg, g0, g1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+    e[i] = pk2(e0, e1);
+    a[i] = pk2(fabsf(x0), fabsf(x1));
+    u[i] = fma2(dup2(c[10]), a[i], dup2(c[9]));
+  }
+#pragma unroll
+  for (int k = 8; k >= 0; --k)
+#pragma unroll
+    for (int i = 0; i < N; ++i) u[i] = fma2(u[i], a[i], dup2(c[k]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) u[i] = mul2(u[i], e[i]);
 }
-// gelu of two values
-__device__ __forceinline__ f32x2 tpg_gelu2(f32x2 x) {
-  f32x2 e, a;
-  const f32x2 u = tpg_core(x, e, a);
-  float x0, x1;
-  unpk2(x, x0, x1);
-  return fma2(u, a, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+// gelu of N pairs
+template <int N>
+__device__ __forceinline__ void tpg_gelu2(const f32x2 (&x)[N], f32x2 (&g)[N]) {
+  f32x2 u[N], e[N], a[N];
+  tpg_core<N>(x, u, e, a);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float x0, x1;
+    unpk2(x[i], x0, x1);
+    g[i] = fma2(u[i], a[i], pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  }
 }
-// gelu and gelu' of two values
-__device__ __forceinline__ void tpg_gelu_pair2(f32x2 x, f32x2& g, f32x2& dg) {
-  f32x2 e, a;
-  const f32x2 u = tpg_core(x, e, a);  // -erfc/2 in [-0.5, 0)
-  float x0, x1, w0, w1;
-  unpk2(x, x0, x1);
-  unpk2(add2(u, dup2(0.5f)), w0, w1);  // 1/2 - erfc/2 >= 0
-  const f32x2 phi = add2(pk2(copysignf(w0, x0), copysignf(w1, x1)), dup2(0.5f));
-  g = mul2(x, phi);
-  dg = fma2(mul2(x, dup2(0.3989422804014327f)), e, phi);
+// gelu and gelu' of N pairs
+template <int N>
+__device__ __forceinline__ void tpg_gelu_pair2(const f32x2 (&x)[N], f32x2 (&g)[N], f32x2 (&dg)[N]) {
+  f32x2 u[N], e[N], a[N];
+  tpg_core<N>(x, u, e, a);  // u = -erfc/2 in [-0.5, 0)
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float x0, x1, w0, w1;
+    unpk2(x[i], x0, x1);
+    unpk2(add2(u[i], dup2(0.5f)), w0, w1);  // 1/2 - erfc/2 >= 0
+    const f32x2 phi = add2(pk2(copysignf(w0, x0), copysignf(w1, x1)), dup2(0.5f));
+    g[i] = mul2(x[i], phi);
+    dg[i] = fma2(mul2(x[i], dup2(0.3989422804014327f)), e[i], phi);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -454,17 +472,19 @@ __device__ __forceinline__ void tp_mma_block(float (&acc)[TP_MT][4][4], const fl
         al[mt][2] = tm_trunc_lo(yb[h][mt].x), al[mt][3] = tm_trunc_lo(yb[h][mt].y);
       }
       const float4* line = p4t + (h * (TP_KB / 8) + ks) * TP_ROWS * 4;
+      float4 b4[4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const float4 b4 = line[nt * 32];
-        const uint32_t bh[2] = {__float_as_uint(b4.x), __float_as_uint(b4.y)};
-        const uint32_t bl[2] = {__float_as_uint(b4.z), __float_as_uint(b4.w)};
+      for (int nt = 0; nt < 4; ++nt) b4[nt] = line[nt * 32];
+      // split terms outermost: the three MMAs on one accumulator are eight instructions apart (HMMA latency is ~3 issue slots)
 #pragma unroll
-        for (int mt = 0; mt < TP_MT; ++mt) mma_tf32_16x8x8(acc[mt][nt], al[mt], bh);
+      for (int term = 0; term < 3; ++term) {
 #pragma unroll
-        for (int mt = 0; mt < TP_MT; ++mt) mma_tf32_16x8x8(acc[mt][nt], ah[mt], bl);
+        for (int nt = 0; nt < 4; ++nt) {
+          const uint32_t bh[2] = {__float_as_uint(b4[nt].x), __float_as_uint(b4[nt].y)};
+          const uint32_t bl[2] = {__float_as_uint(b4[nt].z), __float_as_uint(b4[nt].w)};
 #pragma unroll
-        for (int mt = 0; mt < TP_MT; ++mt) mma_tf32_16x8x8(acc[mt][nt], ah[mt], bh);
+          for (int mt = 0; mt < TP_MT; ++mt) mma_tf32_16x8x8(acc[mt][nt], term == 0 ? al[mt] : ah[mt], term == 1 ? bl : bh);
+        }
       }
     }
   }
@@ -509,7 +529,7 @@ __host__ __device__ inline size_t tp_fwd_smem_bytes(int nh, int M, int C, int O,
 // A CTA walks its tiles in rounds of `round` (<= nwarps): warp w prepares tile w of the round (phase 1), then every warp
 // contracts its sample(s) against every prepared tile (phase 2).  NO as in tail_mma_fwd_kernel.
 template <int NH, int NO>
-__global__ void __launch_bounds__(32 * TP_MAX_WARPS, 3) tail_plan_fwd_kernel(const TailParams P, const TailPlanDev V) {
+__global__ void __launch_bounds__(32 * TP_MAX_WARPS, TP_FWD_CTAS) tail_plan_fwd_kernel(const TailParams P, const TailPlanDev V) {
   const int n_out = NO == 1 ? 1 : P.O;
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TpTile<NH, false>;
@@ -592,14 +612,12 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 3) tail_plan_fwd_kernel(con
           const int c0 = ch * TP_CHUNK + TP_TPC * g;  // this thread's four hidden channels
           const float* y_chunk = P.y + (size_t)(active ? b : 0) * P.M * NH * P.C + c0;
           float acc[TP_MT][4][4];
-          {
-            const float4 bias = *reinterpret_cast<const float4*>(par + c0);  // the accumulators start from the bias b1
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-              acc[0][nt][0] = acc[0][nt][1] = bias.x, acc[0][nt][2] = acc[0][nt][3] = bias.y;
-              acc[1][nt][0] = acc[1][nt][1] = bias.z, acc[1][nt][2] = acc[1][nt][3] = bias.w;
-            }
-          }
+          for (int mt = 0; mt < TP_MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
           for (int kb = 0; kb < nkb; ++kb) {
             if (nkb > 1) {  // rare: more than 16 candidates -> rebuild block kb in place (CTA-uniform branch)
               __syncthreads();
@@ -615,23 +633,30 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 3) tail_plan_fwd_kernel(con
             if (active) tp_mma_block<NH>(acc, T->p4 + p4_lane, cand, cnt, kb, y_chunk, P.C, t);
           }
           if (!active) continue;
-          // epilogue of the chunk: part[o][rows] += W2[o, c] gelu(pre[c]) over the thread's four channels, two rows per op
+          // epilogue of the chunk: part[o][rows] += W2[o, c] gelu(b1[c] + pre[c]) over the thread's four channels, two rows per op
+          const float4 b1v = *reinterpret_cast<const float4*>(par + c0);
           const float4 w2v0 = *reinterpret_cast<const float4*>(par + P.C + c0);
 #pragma unroll
           for (int mt = 0; mt < TP_MT; ++mt) {
+            f32x2 x[8], hid[8];  // [half][nt]: eight independent GELU chains
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              f32x2 hid[4];
+              const int i = 2 * mt + half;
+              const f32x2 bias = dup2(i == 0 ? b1v.x : i == 1 ? b1v.y : i == 2 ? b1v.z : b1v.w);
 #pragma unroll
-              for (int nt = 0; nt < 4; ++nt) hid[nt] = tpg_gelu2(pk2(acc[mt][nt][half * 2], acc[mt][nt][half * 2 + 1]));
+              for (int nt = 0; nt < 4; ++nt) x[half * 4 + nt] = add2(pk2(acc[mt][nt][half * 2], acc[mt][nt][half * 2 + 1]), bias);
+            }
+            tpg_gelu2<8>(x, hid);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int i = 2 * mt + half;
 #pragma unroll
               for (int o = 0; o < NO; ++o) {
                 if (o < n_out) {
-                  const int i = 2 * mt + half;
                   const float wv = o == 0 ? (i == 0 ? w2v0.x : i == 1 ? w2v0.y : i == 2 ? w2v0.z : w2v0.w) : par[(1 + o) * P.C + c0 + i];
                   const f32x2 wv2 = dup2(wv);
 #pragma unroll
-                  for (int nt = 0; nt < 4; ++nt) part[o][nt] = fma2(wv2, hid[nt], part[o][nt]);
+                  for (int nt = 0; nt < 4; ++nt) part[o][nt] = fma2(wv2, hid[half * 4 + nt], part[o][nt]);
                 }
               }
             }
@@ -664,7 +689,7 @@ struct TpBwdSmem {
   float* slot_acc;       // [n_slots][NH][W], 16-byte groups rotated inside 128-byte windows by the slot index
   float* par;            // [C + O*C]: b1 then W2
   float* gpar;           // [C + O*C]: CTA-level reduction of d_b1, d_w2
-  float* red;            // [TP_MAX_WARPS]
+  float* red;            // [TP_BWD_MAX_WARPS]
   int16_t* slot_j;       // [n_slots] slot -> column (-1: free)
   int16_t* bind;         // [TP_BWD_ROUND][M] position in the tile's candidate list -> slot (-1: unbound)
   int16_t* evict;        // [n_slots] column to flush before the slot is reused this round (-1: none)
@@ -759,7 +784,7 @@ __device__ __forceinline__ void tp_flush_cells(const TailParams& P, const TpBwdS
 }
 
 template <int NH, int NO>
-__global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(const TailParams P, const TailPlanDev V) {
+__global__ void __launch_bounds__(32 * TP_BWD_MAX_WARPS, 1) tail_plan_bwd_kernel(const TailParams P, const TailPlanDev V) {
   const int n_out = NO == 1 ? 1 : P.O;
   extern __shared__ __align__(16) unsigned char tall_smem_raw[];
   using Tile = TpTile<NH, true>;
@@ -803,6 +828,7 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
       for (int o = 0; o <= NO; ++o) gacc[a][i][o] = 0.f;
 
   const int cps = P.C / TP_CHUNK;
+  const int units = P.B * cps;  // (sample, 32-column chunk) pairs; warp w takes units w, w + nwarps, ...
   const int tile_begin = blockIdx.x * V.tiles_per_cta;
   const int tile_end = min(V.n_tiles, tile_begin + V.tiles_per_cta);
   using Stage = TpStage<NH, true>;
@@ -866,8 +892,10 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
     for (int sidx = t; sidx < P.n_slots; sidx += 4) {
       const int j = S.evict[sidx];
       if (j < 0) continue;
-      for (int b = warp; b < P.B; b += nwarps)
-        for (int ch = 0; ch < cps; ++ch) tp_flush_cells<NH>(P, S, W, sidx, j, b, ch * TP_CHUNK + TP_TPC * g, b * P.C + ch * TP_CHUNK + TP_TPC * g);
+      for (int u = warp; u < units; u += nwarps) {
+        const int b = u / cps, ch = u - b * cps;
+        tp_flush_cells<NH>(P, S, W, sidx, j, b, ch * TP_CHUNK + TP_TPC * g, b * P.C + ch * TP_CHUNK + TP_TPC * g);
+      }
     }
     __syncwarp();
     // ---- phase 2 ----
@@ -877,9 +905,10 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
       const int16_t* bind = S.bind + v * (cand_stride / 2);
       const int cnt = T->cnt;
       const int nkb = (cnt + TP_KB - 1) / TP_KB;
-      for (int b0 = 0; b0 < P.B; b0 += nwarps) {
-        const int b = b0 + warp;
-        const bool active = b < P.B;
+      for (int u0 = 0; u0 < units; u0 += nwarps) {
+        const int u = u0 + warp;
+        const bool active = u < units;
+        const int b = active ? u / cps : 0, ch = active ? u - b * cps : 0;
         // upstream gradient of this thread's eight tile rows, as pairs (8nt + 2t, 8nt + 2t + 1)
         f32x2 go[4][NO];
 #pragma unroll
@@ -890,10 +919,10 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
             const float g0 = (active && o < n_out && r0 >= 0) ? __ldg(P.d_out + ((int64_t)b * P.N + r0) * n_out + o) : 0.f;
             const float g1 = (active && o < n_out && r1 >= 0) ? __ldg(P.d_out + ((int64_t)b * P.N + r1) * n_out + o) : 0.f;
             go[nt][o] = pk2(g0, g1);
-            if (g == 0) db2[o] += g0 + g1;
+            if (g == 0 && ch == 0) db2[o] += g0 + g1;
           }
         }
-        for (int ch = 0; ch < cps; ++ch) {
+        {
           const int c0 = ch * TP_CHUNK + TP_TPC * g;
           const int xcol = b * P.C + c0;
           const float* y_chunk = P.y + (size_t)(active ? b : 0) * P.M * NH * P.C + c0;
@@ -903,8 +932,8 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[mt][nt][e] = S.par[c0 + 2 * mt + (e >> 1)];
-          // (a) hidden pre-activation, as in the forward
+              for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+          // (a) hidden pre-activation (without the bias), as in the forward
           for (int kb = 0; kb < nkb; ++kb) {
             if (nkb > 1) {
               __syncthreads();
@@ -919,7 +948,10 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
             }
             if (active) tp_mma_block<NH>(acc, T->p4 + p4_lane, cand, cnt, kb, y_chunk, P.C, t);
           }
-          // (b) g1 = gelu'(pre) * (W2^T dOut[b, row, :]) in place; parameter-gradient partials (two rows per packed op)
+          // (b) g1 = gelu'(b1 + pre) * (W2^T dOut[b, row, :]); parameter-gradient partials (two rows per packed op).
+          //     ga[mt][nt] receives g1 directly in the A-fragment order of the products below: accumulator entries
+          //     (e0, e2, e1, e3) = (column g | row 2t, column g+8 | row 2t, column g | row 2t+1, column g+8 | row 2t+1)
+          float ga[TP_MT][4][4];
           if (active) {
 #pragma unroll
             for (int mt = 0; mt < TP_MT; ++mt) {
@@ -927,37 +959,42 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
               for (int half = 0; half < 2; ++half) {
                 const int i = 2 * mt + half;
                 const int c = c0 + i;
+                const f32x2 bias = dup2(S.par[c]);
                 f32x2 wv[NO], dw[NO];
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
                   wv[o] = dup2(o < n_out ? S.par[(1 + o) * P.C + c] : 0.f);
                   dw[o] = 0ull;
                 }
-                f32x2 gsum = 0ull;
+                f32x2 x[4], hid[4], dhid[4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) x[nt] = add2(pk2(acc[mt][nt][half * 2], acc[mt][nt][half * 2 + 1]), bias);
+                tpg_gelu_pair2<4>(x, hid, dhid);
+                float gsum = 0.f;
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
-                  f32x2 hid, dhid;
-                  tpg_gelu_pair2(pk2(acc[mt][nt][half * 2], acc[mt][nt][half * 2 + 1]), hid, dhid);
                   f32x2 up = 0ull;
 #pragma unroll
                   for (int o = 0; o < NO; ++o) {
                     if (o < n_out) {
                       up = fma2(go[nt][o], wv[o], up);
-                      dw[o] = fma2(go[nt][o], hid, dw[o]);
+                      dw[o] = fma2(go[nt][o], hid[nt], dw[o]);
                     }
                   }
-                  const f32x2 g1 = mul2(up, dhid);
-                  unpk2(g1, acc[mt][nt][half * 2], acc[mt][nt][half * 2 + 1]);
-                  gsum = add2(gsum, g1);
+                  float u0, u1, d0, d1;
+                  unpk2(up, u0, u1);
+                  unpk2(dhid[nt], d0, d1);
+                  ga[mt][nt][half] = u0 * d0;      // row 2t   (k-slot t)
+                  ga[mt][nt][2 + half] = u1 * d1;  // row 2t+1 (k-slot t+4)
+                  gsum += ga[mt][nt][half] + ga[mt][nt][2 + half];
                 }
-                float s0, s1;
-                unpk2(gsum, s0, s1);
 #pragma unroll
                 for (int a = 0; a < TP_MAX_CPS; ++a) {
                   if (a == ch) {
-                    gacc[a][i][0] += s0 + s1;
+                    gacc[a][i][0] += gsum;
 #pragma unroll
                     for (int o = 0; o < NO; ++o) {
+                      float s0, s1;
                       unpk2(dw[o], s0, s1);
                       gacc[a][i][1 + o] += s0 + s1;
                     }
@@ -982,6 +1019,7 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
             if (!active) continue;
             const int base = kb * TP_KB;
             const int groups8 = (min(cnt - base, TP_KB) + 7) >> 3;
+            const float4* pz_lane = reinterpret_cast<const float4*>(T->pz + g * TP_ZP + t * 8);
             for (int ct = 0; ct < groups8; ++ct) {
               // this thread's two candidates of the group: 8ct + 2t + e
               bool live[2];
@@ -993,6 +1031,16 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
                 jj[e] = live[e] ? (int)cand[ci] : 0;
                 sidx[e] = live[e] ? (int)bind[ci] : -1;
               }
+              // Y rows of the two candidates for the scale gradient: requested before the products so that the trip to L2
+              // overlaps the 48 MMAs of each head (dead candidates read row 0 and are skipped below)
+              float4 yv[2][NH];
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int h = 0; h < NH; ++h)
+                  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                               : "=f"(yv[e][h].x), "=f"(yv[e][h].y), "=f"(yv[e][h].z), "=f"(yv[e][h].w)
+                               : "l"(y_chunk + ((size_t)jj[e] * NH + h) * P.C));
 #pragma unroll
               for (int h = 0; h < NH; ++h) {
                 float dy[TP_MT][4], dz[TP_MT][4];
@@ -1003,32 +1051,36 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                   // B fragments: k-slot t <-> tile row 8nt+2t, k-slot t+4 <-> row 8nt+2t+1; n = candidate 8ct+g
-                  const float4* zp = reinterpret_cast<const float4*>(&T->pz[tp_pz_index(h, ct * 8 + g, 8 * nt + 2 * t)]);
+                  const float4* zp = pz_lane + ((h * TP_KB + ct * 8) * (TP_ZP / 4) + nt * 8);
                   const float4 pq = zp[0], zq = zp[1];
                   const uint32_t ph[2] = {__float_as_uint(pq.x), __float_as_uint(pq.y)};
                   const uint32_t pl[2] = {__float_as_uint(pq.z), __float_as_uint(pq.w)};
                   const uint32_t zh[2] = {__float_as_uint(zq.x), __float_as_uint(zq.y)};
                   const uint32_t zl[2] = {__float_as_uint(zq.z), __float_as_uint(zq.w)};
-                  // A fragments: the accumulator registers of g1^T, reordered (m = column, k = row)
+                  // A fragments: g1^T in fragment order (m = column, k = row), hi = the raw value, lo = its truncation residual
+                  uint32_t al[TP_MT][4], ah[TP_MT][4];
 #pragma unroll
-                  for (int mt = 0; mt < TP_MT; ++mt) {
-                    const float a0 = acc[mt][nt][0], a1 = acc[mt][nt][2], a2 = acc[mt][nt][1], a3 = acc[mt][nt][3];
-                    const uint32_t al[4] = {tm_trunc_lo(a0), tm_trunc_lo(a1), tm_trunc_lo(a2), tm_trunc_lo(a3)};
-                    const uint32_t ah[4] = {__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3)};
-                    mma_tf32_16x8x8(dy[mt], al, ph);
-                    mma_tf32_16x8x8(dz[mt], al, zh);
-                    mma_tf32_16x8x8(dy[mt], ah, pl);
-                    mma_tf32_16x8x8(dz[mt], ah, zl);
-                    mma_tf32_16x8x8(dy[mt], ah, ph);
-                    mma_tf32_16x8x8(dz[mt], ah, zh);
+                  for (int mt = 0; mt < TP_MT; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      ah[mt][i] = __float_as_uint(ga[mt][nt][i]);
+                      al[mt][i] = tm_trunc_lo(ga[mt][nt][i]);
+                    }
+                  // split terms outermost: consecutive MMAs on one accumulator are four instructions apart
+#pragma unroll
+                  for (int term = 0; term < 3; ++term) {
+#pragma unroll
+                    for (int mt = 0; mt < TP_MT; ++mt) {
+                      mma_tf32_16x8x8(dy[mt], term == 0 ? al[mt] : ah[mt], term == 1 ? pl : ph);
+                      mma_tf32_16x8x8(dz[mt], term == 0 ? al[mt] : ah[mt], term == 1 ? zl : zh);
+                    }
                   }
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   if (!live[e]) continue;
                   // scale gradient: -sum_col Y_h[j, col] dZ[col, j]
-                  const float4 yv = __ldg(reinterpret_cast<const float4*>(y_chunk + ((size_t)jj[e] * NH + h) * P.C));
-                  ds_head[h] += yv.x * dz[0][e] + yv.y * dz[0][2 + e] + yv.z * dz[1][e] + yv.w * dz[1][2 + e];
+                  ds_head[h] += yv[e][h].x * dz[0][e] + yv[e][h].y * dz[0][2 + e] + yv[e][h].z * dz[1][e] + yv[e][h].w * dz[1][2 + e];
                   // value gradient: the quad owns these cells of the slot (or adds to d_y itself if the column is unbound)
                   const float4 add = make_float4(dy[0][e], dy[0][2 + e], dy[1][e], dy[1][2 + e]);
                   if (sidx[e] >= 0) {
@@ -1053,8 +1105,10 @@ __global__ void __launch_bounds__(32 * TP_MAX_WARPS, 2) tail_plan_bwd_kernel(con
   for (int sidx = t; sidx < P.n_slots; sidx += 4) {
     const int j = S.slot_j[sidx];
     if (j < 0) continue;
-    for (int b = warp; b < P.B; b += nwarps)
-      for (int ch = 0; ch < cps; ++ch) tp_flush_cells<NH>(P, S, W, sidx, j, b, ch * TP_CHUNK + TP_TPC * g, b * P.C + ch * TP_CHUNK + TP_TPC * g);
+    for (int u = warp; u < units; u += nwarps) {
+      const int b = u / cps, ch = u - b * cps;
+      tp_flush_cells<NH>(P, S, W, sidx, j, b, ch * TP_CHUNK + TP_TPC * g, b * P.C + ch * TP_CHUNK + TP_TPC * g);
+    }
   }
 
   // ---- parameter gradients: one reduction per CTA ----

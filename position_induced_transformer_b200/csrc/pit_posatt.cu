@@ -495,8 +495,8 @@ TallPlan plan_tail_plan_fwd(const pit_problem_t* p, int out_dim, const pit_tail_
   TallPlan c{};
   if (!tail_plan_eligible(p, out_dim, plan)) return c;
   const int warps = p->batch < pit::TP_MAX_WARPS ? p->batch : pit::TP_MAX_WARPS;
-  c.l4 = warps < 4 ? warps : 4;  // tiles per round (kept in l4): 4 keeps three CTAs per SM at ~37 KB each and leaves most of the 228 KB to L1
-  plan_tail_plan_grid(p, plan, c, 3, c.l4);
+  c.l4 = warps < 8 ? warps : 8;  // tiles per round (kept in l4): 4 keeps three CTAs per SM at ~37 KB each and leaves most of the 228 KB to L1
+  plan_tail_plan_grid(p, plan, c, pit::TP_FWD_CTAS, c.l4);
   c.smem = pit::tp_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim, c.l4);
   if (c.smem > (size_t)max_smem_optin() - 1024) return c;
   c.ok = true;
@@ -506,22 +506,24 @@ TallPlan plan_tail_plan_fwd(const pit_problem_t* p, int out_dim, const pit_tail_
 TallPlan plan_tail_plan_bwd(const pit_problem_t* p, int out_dim, const pit_tail_plan_t* plan) {
   TallPlan c{};
   if (!tail_plan_eligible(p, out_dim, plan)) return c;
-  plan_tail_plan_grid(p, plan, c, 2, pit::TP_BWD_ROUND);
+  // one CTA per SM, one warp per (sample, 32-column chunk), at most 16: a single set of tiles and slots per SM leaves
+  // ~96 KB of the 228 KB to L1, which is what keeps the gathered Y rows of the current tiles on chip
+  const int units = p->batch * (p->dim / pit::TP_CHUNK);
+  const int warps = units < pit::TP_BWD_MAX_WARPS ? units : pit::TP_BWD_MAX_WARPS;
+  c.threads = 32 * warps;
+  const int target = sm_count();
+  c.rows_per_unit = (plan->n_tiles + target - 1) / target;
+  c.grid = (plan->n_tiles + c.rows_per_unit - 1) / c.rows_per_unit;
   const int W = p->batch * p->dim;
   const size_t fixed = pit::tp_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, 0);
   const size_t per_slot = (size_t)p->n_head * W * 4 + 4;
-  for (int per_sm = 2; per_sm >= 1; --per_sm) {
-    const size_t budget = ((size_t)max_smem_optin() + 1024) / per_sm - 2048;
-    if (budget <= fixed) continue;
-    int n = (int)((budget - fixed) / per_slot);
-    if (n > 32) n = 32;
-    if (n > p->n_in) n = p->n_in;
-    if (n >= 12 || n == p->n_in || per_sm == 1) {
-      c.n_slots = n;
-      break;
-    }
-  }
-  if (c.n_slots < 1) return c;
+  const size_t budget = 128 * 1024;
+  int n = budget > fixed ? (int)((budget - fixed) / per_slot) : 0;
+  if (n < 8) n = (int)(((size_t)max_smem_optin() - 2048 - fixed) / per_slot);  // wide batches: whatever fits
+  if (n > 32) n = 32;
+  if (n > p->n_in) n = p->n_in;
+  if (n < 1) return c;
+  c.n_slots = n;
   c.smem = pit::tp_bwd_smem_bytes(p->n_head, p->n_in, W, p->dim, out_dim, c.n_slots);
   if (c.smem > (size_t)max_smem_optin() - 1024) return c;
   c.ok = true;

@@ -1,10 +1,10 @@
-"""The five BASELINE.json workloads as (model, synthetic batch) factories.
+"""The reference's experiment configurations as (model, synthetic batch) factories.
 
 Each model class adds the ``forward`` that the corresponding reference script wraps around
 ``encoder / processor / decoder`` (train_burgers.py:40-49, train_sod.py, train_darcy.py:46-59,
-train_elasticity.py:41-54, train_naca.py:47-65); each ``make_*`` function returns the model with
-the script's hyper-parameters and a deterministic synthetic batch of the dataset's shape
-(the datasets themselves are not distributable: SURVEY.md section 2 #16).
+train_elasticity.py:41-54, train_naca.py:47-65, train_vorticity.py:44-62, train_cylinder.py:40-52); the
+hyper-parameters, meshes and synthetic batch generators come from ``workload_specs`` (pure data, shared with the
+CPU reference arm of bench.py, which must not load the CUDA library).
 """
 from __future__ import annotations
 
@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import pit as P
+from . import workload_specs as WS
 from .utils import RelLpNorm
 
 
@@ -44,8 +45,32 @@ class DarcyPiT(SharedMeshPiT, P.pit_fixed):
     pass
 
 
-class VorticityPiT(SharedMeshPiT, P.pit_periodic2d):
-    pass
+class VorticityPiT(P.pit_periodic2d):
+    """Periodic 2-D vorticity model with an instance norm after the encoder and after the processor
+    (train_vorticity.py:43, 56-59)."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.norm = torch.nn.InstanceNorm1d(self.hid_dim)
+
+    def forward(self, mesh_in, func_in, mesh_out):
+        lead = mesh_out.shape[:-1]
+        mesh_in = mesh_in.reshape(-1, self.space_dim)
+        mesh_out = mesh_out.reshape(-1, self.space_dim)
+        func_in = func_in.reshape(func_in.shape[0], -1, self.in_dim)
+        feats = torch.cat((mesh_in.unsqueeze(0).expand(func_in.shape[0], -1, -1), func_in), dim=-1)
+        latent = self.encoder(mesh_in, feats, self.mesh_ltt)
+        latent = self.norm(latent.permute(0, 2, 1)).permute(0, 2, 1)
+        latent = self.processor(latent, self.mesh_ltt)
+        latent = self.norm(latent.permute(0, 2, 1)).permute(0, 2, 1)
+        return self.decoder(self.mesh_ltt, latent, mesh_out).reshape(func_in.shape[0], *lead, self.out_dim)
+
+
+class CylinderPiT(SharedMeshPiT, P.pit_fixed):
+    """Unstructured wake mesh; the model predicts the increment (train_cylinder.py:40-52: `return func_out + x`)."""
+
+    def forward(self, mesh_in, func_in, mesh_out):
+        return SharedMeshPiT.forward(self, mesh_in, func_in, mesh_out) + func_in
 
 
 class ElasticityPiT(P.pit):
@@ -90,6 +115,8 @@ class Workload:
     loss: Callable
     meshes: tuple = ()          # tensors that stay resident on the device across steps (not per-step input)
     note: str = ""
+    rollout: int = 1            # autoregressive model applications per training step (train_vorticity.py:122-126)
+    spec: WS.Spec = None
 
     def to(self, device):
         self.model.to(device)
@@ -99,104 +126,50 @@ class Workload:
         return self
 
 
-def grid_points(n: int, lo: float = 0.0, hi: float = 1.0) -> torch.Tensor:
-    """(n*n, 2) fp32 grid built like train_darcy.py:83-88 (float64 linspace, meshgrid, cast)."""
-    ax = np.linspace(lo, hi, n)
-    return torch.tensor(np.vstack([g.ravel() for g in np.meshgrid(ax, ax)]).T, dtype=torch.float)
+_MODEL_CLASS = {"burgers": BurgersPiT, "sod": SodPiT, "darcy421": DarcyPiT, "darcy43": DarcyPiT, "elasticity": ElasticityPiT,
+                "naca": NacaPiT, "vorticity": VorticityPiT, "cylinder": CylinderPiT}
+
+
+def make(name: str, batch: int = 0, spec: WS.Spec = None) -> Workload:
+    """Model with the script's hyper-parameters (seeded like pit.py:3) and the synthetic batch generator of `name`
+    (`spec` overrides the stock one, e.g. a shorter vorticity rollout)."""
+    spec = spec or WS.SPECS[name]()
+    torch.manual_seed(0)
+    sd, in_dim, out_dim, hid, heads, blocks, en_loc, de_loc = spec.ctor
+    kw = {}
+    if name == "naca":
+        kw = {"x_downsample": spec.extra["x_down"], "y_downsample": spec.extra["y_down"]}
+    model = _MODEL_CLASS[name](sd, in_dim, out_dim, hid, heads, blocks, spec.mesh_ltt, en_loc, de_loc, **kw)
+    meshes = () if spec.mesh is None else (spec.mesh,)
+    return Workload(spec.name, model, batch or spec.batch, spec.make_batch, RelLpNorm(*spec.loss), meshes, spec.source, spec.rollout, spec)
 
 
 def make_burgers(batch: int = 8) -> Workload:
-    torch.manual_seed(0)
-    mesh = torch.linspace(0, 1, 1025)[:-1].reshape(-1, 1)
-    ltt = torch.linspace(0, 1, 257)[:-1].reshape(-1, 1)
-    model = BurgersPiT(1, 1, 1, 64, 2, 5, ltt, 0.02, 0.02)
-
-    def batch_fn(gen, b):
-        return (torch.randn(b, 1024, 1, generator=gen),), torch.randn(b, 1024, 1, generator=gen)
-
-    return Workload("burgers_1024", model, batch, batch_fn, RelLpNorm(1, 1), (mesh,), "train_burgers.py:51-80")
+    return make("burgers", batch)
 
 
 def make_sod(batch: int = 8) -> Workload:
-    torch.manual_seed(0)
-    mesh = torch.linspace(-5, 5, 2049)[:-1].reshape(-1, 1)
-    ltt = torch.linspace(-5, 5, 257)[:-1].reshape(-1, 1)
-    model = SodPiT(1, 3, 3, 32, 1, 2, ltt, 0.02, 0.02)
-
-    def batch_fn(gen, b):
-        return (torch.rand(b, 2048, 3, generator=gen) * 0.9 + 0.1,), torch.rand(b, 2048, 3, generator=gen) * 0.9 + 0.1
-
-    return Workload("sod_2048", model, batch, batch_fn, RelLpNorm(3, 2), (mesh,), "train_sod.py:55-76")
+    return make("sod", batch)
 
 
 def make_darcy(side: int = 421, batch: int = 8) -> Workload:
+    if side in (421, 43):
+        return make(f"darcy{side}", batch)
+    spec = WS.darcy(side)
     torch.manual_seed(0)
-    mesh = grid_points(side).reshape(side, side, 2)
-    ltt = grid_points(16).reshape(16, 16, 2)
-    model = DarcyPiT(2, 1, 1, 64, 2, 4, ltt, 0.02, 0.02)
-
-    def batch_fn(gen, b):
-        # piecewise-constant coefficient field {3, 12} from a blurred Gaussian field, then standardised
-        # (the real a(x) is a thresholded GRF; train_darcy.py:75-79 normalises it pixel-wise)
-        field = torch.randn(b, 1, side, side, generator=gen)
-        k = 9
-        field = torch.nn.functional.avg_pool2d(field, k, stride=1, padding=k // 2)
-        coeff = torch.where(field > 0, 12.0, 3.0).reshape(b, side, side, 1)
-        coeff = (coeff - 7.5) / 4.5
-        target = torch.rand(b, side, side, 1, generator=gen) * 0.013 + 1e-4
-        return (coeff,), target
-
-    return Workload(f"darcy_{side}x{side}", model, batch, batch_fn, RelLpNorm(1, 2), (mesh,), "train_darcy.py:62-111")
+    model = DarcyPiT(*spec.ctor[:6], spec.mesh_ltt, *spec.ctor[6:])
+    return Workload(spec.name, model, batch, spec.make_batch, RelLpNorm(*spec.loss), (spec.mesh,), spec.source, 1, spec)
 
 
-def make_elasticity(batch: int = 10, points: int = 972) -> Workload:
-    torch.manual_seed(0)
-    model = ElasticityPiT(2, 44, 1, 256, 2, 4, None, 0.02, 0.02)
-
-    def batch_fn(gen, b):
-        # unit-cell point cloud with a central void of random radius, 42 global shape codes broadcast to the points
-        ang = torch.rand(b, points, generator=gen) * 2 * np.pi
-        hole = 0.2 + 0.2 * torch.rand(b, 1, generator=gen)
-        rad = hole + (0.7 - hole) * torch.sqrt(torch.rand(b, points, generator=gen))
-        xy = 0.5 + torch.stack((rad * torch.cos(ang), rad * torch.sin(ang)), -1).clamp(-0.5, 0.5)
-        codes = torch.rand(b, 1, 42, generator=gen).expand(b, points, 42)
-        return (xy, torch.cat((xy, codes), -1), xy), torch.rand(b, points, 1, generator=gen) + 0.5
-
-    return Workload(f"elasticity_{points}", model, batch, batch_fn, RelLpNorm(1, 2), (), "train_elasticity.py:56-96")
+def make_elasticity(batch: int = 10) -> Workload:
+    return make("elasticity", batch)
 
 
 def make_naca(batch: int = 20) -> Workload:
-    torch.manual_seed(0)
-    model = NacaPiT(2, 2, 4, 128, 1, 4, None, 0.02, 0.02)
-
-    def batch_fn(gen, b):
-        # NACA 4-digit-like airfoil polyline (120 points) and a 221 x 51 O-grid growing out of it
-        t = torch.linspace(0, 2 * np.pi, 121)[:-1]
-        thick = 0.08 + 0.1 * torch.rand(b, 1, generator=gen)
-        camber = 0.04 * torch.rand(b, 1, generator=gen)
-        xs = 0.5 + 0.5 * torch.cos(t).unsqueeze(0).expand(b, -1)
-        ys = thick * torch.sin(t).unsqueeze(0) * torch.sqrt(xs.clamp_min(1e-4)) * (1 - xs) * 3 + camber * torch.sin(np.pi * xs)
-        foil = torch.stack((xs, ys), -1)
-        t2 = torch.linspace(0, 2 * np.pi, 221)
-        x2 = 0.5 + 0.5 * torch.cos(t2).unsqueeze(0).expand(b, -1)
-        y2 = thick * torch.sin(t2).unsqueeze(0) * torch.sqrt(x2.clamp_min(1e-4)) * (1 - x2) * 3 + camber * torch.sin(np.pi * x2)
-        inner = torch.stack((x2, y2), -1)                                        # (b, 221, 2)
-        outer = torch.stack((0.5 + 3 * torch.cos(t2), 3 * torch.sin(t2)), -1)     # (221, 2)
-        s = (torch.linspace(0, 1, 51) ** 2).reshape(1, 1, 51, 1)
-        grid = inner.unsqueeze(2) * (1 - s) + outer.reshape(1, 221, 1, 2) * s     # (b, 221, 51, 2)
-        return (foil, foil.clone(), grid), torch.rand(b, 221, 51, 4, generator=gen) + 0.5
-
-    return Workload("naca_221x51", model, batch, batch_fn, RelLpNorm(4, 2), (), "train_naca.py:68-110")
+    return make("naca", batch)
 
 
-WORKLOADS = {
-    "burgers": make_burgers,
-    "sod": make_sod,
-    "darcy421": lambda batch=8: make_darcy(421, batch),
-    "darcy43": lambda batch=8: make_darcy(43, batch),
-    "elasticity": make_elasticity,
-    "naca": make_naca,
-}
+WORKLOADS = {name: (lambda batch=0, _n=name: make(_n, batch)) for name in WS.SPECS}
 
 
 def run_model(w: Workload, inputs):
@@ -204,3 +177,16 @@ def run_model(w: Workload, inputs):
     if w.meshes:                       # shared mesh: model(mesh, x, mesh)
         return w.model(w.meshes[0], inputs[0], w.meshes[0])
     return w.model(*inputs)
+
+
+def step_loss(w: Workload, inputs, target):
+    """Loss of one training step as the script forms it: one model application, or -- vorticity -- an unrolled rollout in
+    which every prediction is appended to the input window and the per-step losses are summed (train_vorticity.py:122-126)."""
+    if w.rollout == 1:
+        return w.loss(target, run_model(w, inputs))
+    x, loss = inputs[0], 0.0
+    for t in range(w.rollout):
+        out = run_model(w, (x,))
+        loss = loss + w.loss(out, target[..., t:t + 1])
+        x = torch.cat((x[..., 1:], out), dim=-1)
+    return loss
