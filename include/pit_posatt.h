@@ -69,6 +69,19 @@ typedef struct pit_rowstat {
   int32_t masked;     /* 0: locality >= 1, every column kept; 1: apply the quantile mask */
 } pit_rowstat_t;
 
+/* Tile plan of a mesh pair (described with pit_tail_plan_rows / pit_tail_plan_fill below). */
+#define PIT_PLAN_ROWS 0    /* tiles of mesh_out rows against mesh_in candidates (M <= 1024): decoder stages              */
+#define PIT_PLAN_COLUMNS 1 /* tiles of mesh_in columns against mesh_out candidates (N <= 1024): local encoder stages     */
+
+typedef struct pit_tail_plan {
+  const void* rec;
+  const int32_t* tile_off;
+  const int32_t* tile_cnt;
+  const int16_t* cand;
+  const float* d2;
+  int32_t n_tiles;
+} pit_tail_plan_t;
+
 /* Library identification. */
 int pit_abi_version(void);
 const char* pit_last_error(void);
@@ -96,12 +109,14 @@ int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh
  *        head-major (h*D + d) -- ld_out = H*D, col_off = 0 for a cross stage;
  *        ld_out = (1+H)*D, col_off = D for the self stage with concat (the caller, or
  *        copy_values != 0, fills the first D columns with `values`, which requires N == M);
- *   rowsum [(B),H,N]: sum of unnormalised weights exp(s*v_min - s*d2) of each row (saved for backward).  */
+ *   rowsum [(B),H,N]: sum of unnormalised weights exp(s*v_min - s*d2) of each row (saved for backward).
+ *   column_plan: optional PIT_PLAN_COLUMNS tile plan of the mesh pair (NULL: none), used by masked stages with few rows and a
+ *        huge column set (the local encoder); the same plan must then be passed to pit_posatt_backward.  */
 int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
                        const float* period, const float* values, const float* scale,
                        const pit_rowstat_t* stat, float* out, int64_t ld_out, int64_t col_off,
                        int32_t copy_values, float* rowsum, void* workspace, size_t workspace_bytes,
-                       void* stream);
+                       const pit_tail_plan_t* column_plan, void* stream);
 
 /* Fused backward.  d_out uses the same (ld_out, col_off) addressing as `out`.
  *   d_values [B,M,D]  (may be NULL: not computed).  If accumulate_concat != 0 the first D columns
@@ -112,7 +127,7 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
                         const pit_rowstat_t* stat, const float* rowsum, const float* d_out,
                         int64_t ld_out, int64_t col_off, int32_t accumulate_concat,
                         float* d_values, float* d_scale, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        const pit_tail_plan_t* column_plan, void* stream);
 
 /* Per-head scale map of pit.py:48:  scale[i] = tan(c * (1 + sin(lmda[i]))),  c = fp32(0.25*pi*(1-1e-7)),
  * each operation rounded to fp32 separately as the reference's chain of torch ops does (sin, add, mul, tan:
@@ -161,21 +176,17 @@ int pit_rel_lp_backward(const float* truth, const float* pred, const float* norm
  *                           device->host read of the library's protocol) and allocates `cand` and `d2`;
  *   2. pit_tail_plan_fill   writes cand, d2, rec.  Same workspace as step 1, untouched in between.
  * Requires shared meshes with M <= 1024.  Pass the plan to pit_decoder_tail_forward / _backward (NULL: no plan, the
- * kernels scan the latent mesh themselves). */
-typedef struct pit_tail_plan {
-  const void* rec;
-  const int32_t* tile_off;
-  const int32_t* tile_cnt;
-  const int16_t* cand;
-  const float* d2;
-  int32_t n_tiles;
-} pit_tail_plan_t;
+ * kernels scan the latent mesh themselves).
+ * The same structure with the roles of the meshes exchanged (side = PIT_PLAN_COLUMNS: the mesh_in columns are sorted by the
+ * set of mesh_out rows that can see them; `cand` then holds row indices, rec = {0, 0, 0, column}, d2 the distance of tile
+ * column c to candidate row k) serves the local ENCODER stage (few rows, a huge column set, pit.py:109 at Darcy-421:
+ * 256 x 177 241): pass it to pit_posatt_forward / _backward as `column_plan`. */
 
-size_t pit_tail_plan_workspace_bytes(const pit_problem_t* p);
-int pit_tail_plan_rows(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+size_t pit_tail_plan_workspace_bytes(const pit_problem_t* p, int32_t side);
+int pit_tail_plan_rows(const pit_problem_t* p, int32_t side, const float* mesh_out, const float* mesh_in, const float* period,
                        const pit_rowstat_t* stat, int32_t* tile_off, int32_t* tile_cnt, void* workspace, size_t workspace_bytes,
                        void* stream);
-int pit_tail_plan_fill(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+int pit_tail_plan_fill(const pit_problem_t* p, int32_t side, const float* mesh_out, const float* mesh_in, const float* period,
                        const pit_rowstat_t* stat, const int32_t* tile_off, void* rec, int16_t* cand, float* d2,
                        void* workspace, size_t workspace_bytes, void* stream);
 

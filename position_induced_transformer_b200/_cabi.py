@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
 ABI_VERSION = 5
+PLAN_ROWS, PLAN_COLUMNS = 0, 1
 
 EXPORTS = (
     "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
@@ -56,19 +57,19 @@ def _load() -> C.CDLL:
     lib.pit_workspace_bytes.restype = C.c_size_t
     lib.pit_rowstat.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, i32, i32, f32p, f32p, f32p, p]
     lib.pit_posatt_forward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
-                                       f32p, i64, i64, i32, f32p, p, C.c_size_t, p]
+                                       f32p, i64, i64, i32, f32p, p, C.c_size_t, C.POINTER(TailPlan), p]
     lib.pit_posatt_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat), f32p,
-                                        f32p, i64, i64, i32, f32p, f32p, p, C.c_size_t, p]
+                                        f32p, i64, i64, i32, f32p, f32p, p, C.c_size_t, C.POINTER(TailPlan), p]
     lib.pit_decoder_tail_supported.argtypes = [C.POINTER(Problem), i32]
     lib.pit_decoder_tail_forward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
                                              f32p, f32p, f32p, i32, f32p, f32p, C.POINTER(TailPlan), p]
     lib.pit_decoder_tail_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
                                               f32p, f32p, f32p, i32, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                               C.POINTER(TailPlan), p]
-    lib.pit_tail_plan_workspace_bytes.argtypes = [C.POINTER(Problem)]
+    lib.pit_tail_plan_workspace_bytes.argtypes = [C.POINTER(Problem), i32]
     lib.pit_tail_plan_workspace_bytes.restype = C.c_size_t
-    lib.pit_tail_plan_rows.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, C.POINTER(RowStat), p, p, p, C.c_size_t, p]
-    lib.pit_tail_plan_fill.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, C.POINTER(RowStat), p, p, p, p, p, C.c_size_t, p]
+    lib.pit_tail_plan_rows.argtypes = [C.POINTER(Problem), i32, f32p, f32p, f32p, C.POINTER(RowStat), p, p, p, C.c_size_t, p]
+    lib.pit_tail_plan_fill.argtypes = [C.POINTER(Problem), i32, f32p, f32p, f32p, C.POINTER(RowStat), p, p, p, p, p, C.c_size_t, p]
     lib.pit_head_scale_forward.argtypes = [f32p, f32p, i32, p]
     lib.pit_head_scale_backward.argtypes = [f32p, f32p, f32p, f32p, i32, p]
     lib.pit_bias_act_supported.argtypes = [i64, i32]

@@ -34,7 +34,7 @@ constexpr int TP_CHUNK = 16 * TP_MT;  // hidden-vector columns per warp pass
 constexpr int TP_TPC = 2 * TP_MT;     // contiguous columns a thread owns inside a chunk (one float4)
 constexpr int TP_MAX_WARPS = 8;       // forward: one warp per sample
 constexpr int TP_BWD_MAX_WARPS = 16;  // backward: one warp per (sample, 32-column chunk), one CTA per SM
-constexpr int TP_BWD_ROUND = 4;   // tiles prepared per round in the backward
+constexpr int TP_BWD_ROUND = 2;   // tiles prepared per round in the backward
 constexpr int TP_FWD_CTAS = 2;    // resident forward CTAs per SM the register budget is set for (2: 128 registers, 3: 80)
 
 // Device view of a plan (all pointers into caller-owned buffers, see pit_tail_plan_t in include/pit_posatt.h).
@@ -52,14 +52,20 @@ struct TailPlanDev {
 // ---------------------------------------------------------------------------------------
 // plan construction (once per mesh pair)
 // ---------------------------------------------------------------------------------------
+// The plan tiles the LARGE mesh of a stage against the small one: `mesh_out` below is the tiled side (N points, sorted and
+// cut into tiles of 32), `mesh_in` the small side (M <= 1024 points, the candidates).  For a decoder these are the stage's
+// own mesh_out / mesh_in and the pre-filter radius belongs to the tiled point (its row statistics); for an encoder
+// (`transposed`) the tiled side is the stage's mesh_in (the attention's columns), the candidates are its rows, and the
+// radius -- like all statistics -- belongs to the candidate.
 struct PlanBuildParams {
-  const float* mesh_out;  // [N,sd]
-  const float* mesh_in;   // [M,sd]
+  const float* mesh_out;  // [N,sd] tiled side
+  const float* mesh_in;   // [M,sd] candidate side
   const float* period;
   const float* v_min;
   const float* v_lo;
   const float* v_hi;
   int masked;
+  int transposed;
   int N, M, sd;
   // stage 1
   unsigned long long* keys;  // [N]
@@ -79,6 +85,11 @@ template <int GEO>
 __device__ __forceinline__ float plan_vcap(const PlanBuildParams& P, int row) {
   return P.masked ? __ldg(P.v_hi + row) * 1.000001f : INFINITY;  // same pre-filter radius as tm_row / tall_scan_row
 }
+// d2 in the argument order of the stage (mesh_out point first), whichever side is tiled
+template <int GEO>
+__device__ __forceinline__ float plan_dist2(const PlanBuildParams& P, const Point<GEO>& tiled, const Point<GEO>& cand, float period) {
+  return P.transposed ? dist2<GEO>(cand, tiled, period) : dist2<GEO>(tiled, cand, period);
+}
 
 // Sort key of a row: its four smallest candidate columns (10 bits each) and a hash of the whole set.  Equal sets get
 // equal keys; sets that share their leading columns stay close, which keeps the tiles that straddle two sets small.
@@ -89,15 +100,17 @@ __global__ void __launch_bounds__(128) plan_key_kernel(const PlanBuildParams P) 
   if (row >= P.N) return;
   const float period = P.period ? __ldg(P.period) : 0.f;
   const Point<GEO> o = load_point<GEO>(P.mesh_out, row, P.sd);
-  const float vcap = plan_vcap<GEO>(P, row);
+  const float vcap = P.transposed ? 0.f : plan_vcap<GEO>(P, row);
   unsigned long long lead = 0;
   int found = 0;
   uint32_t hash = 2166136261u;
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
     const int j = c * 32 + lane;
-    const Point<GEO> q = load_point<GEO>(P.mesh_in, j < P.M ? j : 0, P.sd);
-    unsigned m = __ballot_sync(FULL, j < P.M && dist2<GEO>(o, q, period) <= vcap);
+    const int jc = j < P.M ? j : 0;
+    const Point<GEO> q = load_point<GEO>(P.mesh_in, jc, P.sd);
+    const float cap = P.transposed ? plan_vcap<GEO>(P, jc) : vcap;
+    unsigned m = __ballot_sync(FULL, j < P.M && plan_dist2<GEO>(P, o, q, period) <= cap);
     hash = (hash ^ m) * 16777619u;
     hash ^= hash >> 15;
     while (m && found < 4) {
@@ -129,17 +142,24 @@ __global__ void __launch_bounds__(128) plan_tile_kernel(const PlanBuildParams P)
   const int row = slot < P.N ? __ldg(P.perm + slot) : -1;
   const int r = row >= 0 ? row : 0;
   const Point<GEO> o = load_point<GEO>(P.mesh_out, r, P.sd);
-  const float vcap = row >= 0 ? plan_vcap<GEO>(P, r) : -1.f;
+  const float vcap = row < 0 ? -1.f : (P.transposed ? INFINITY : plan_vcap<GEO>(P, r));
   if (FILL) {
-    const float vmin = __ldg(P.v_min + r);
-    const float vlo = P.masked ? __ldg(P.v_lo + r) : 0.f, vhi = P.masked ? __ldg(P.v_hi + r) : 0.f;
-    P.rec[slot] = make_float4(vmin, vlo, vhi, __int_as_float(row));
+    float4 rec = make_float4(0.f, 0.f, 0.f, __int_as_float(row));
+    if (!P.transposed) {
+      rec.x = __ldg(P.v_min + r);
+      rec.y = P.masked ? __ldg(P.v_lo + r) : 0.f;
+      rec.z = P.masked ? __ldg(P.v_hi + r) : 0.f;
+    }
+    P.rec[slot] = rec;
   }
   Point<GEO> col[CPL];
+  float ccap[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
     const int j = c * 32 + lane;
-    col[c] = load_point<GEO>(P.mesh_in, j < P.M ? j : 0, P.sd);
+    const int jc = j < P.M ? j : 0;
+    col[c] = load_point<GEO>(P.mesh_in, jc, P.sd);
+    ccap[c] = P.transposed ? plan_vcap<GEO>(P, jc) : INFINITY;
   }
   uint32_t flags = 0;
   for (int i = 0; i < TP_ROWS; ++i) {
@@ -148,7 +168,7 @@ __global__ void __launch_bounds__(128) plan_tile_kernel(const PlanBuildParams P)
     oi.y = __shfl_sync(FULL, o.y, i);
     const float vc = __shfl_sync(FULL, vcap, i);
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) flags |= (dist2<GEO>(oi, col[c], period) <= vc) ? (1u << c) : 0u;
+    for (int c = 0; c < CPL; ++c) flags |= (plan_dist2<GEO>(P, oi, col[c], period) <= fminf(vc, ccap[c])) ? (1u << c) : 0u;
   }
   int n = 0;
   const unsigned lt = (1u << lane) - 1u;
@@ -167,11 +187,12 @@ __global__ void __launch_bounds__(128) plan_tile_kernel(const PlanBuildParams P)
     P.tile_pad[tile] = (n + 7) & ~7;
   }
   if (FILL) {
-    if (lane < ((n + 7) & ~7) - n) out[n + lane] = 0;  // padding entries (never read as candidates: the count bounds every loop)  // the tile's squared distances, bit-exact as the kernels would evaluate them: lane = row, one 128-byte line per candidate
+    if (lane < ((n + 7) & ~7) - n) out[n + lane] = 0;  // padding entries (never read as candidates: the count bounds every loop)
+    // the tile's squared distances, bit-exact as the kernels would evaluate them: lane = row, one 128-byte line per candidate
     __syncwarp();
     for (int k = 0; k < n; ++k) {
       const Point<GEO> q = load_point<GEO>(P.mesh_in, (int)out[k], P.sd);
-      P.d2[(size_t)(off + k) * TP_ROWS + lane] = dist2<GEO>(o, q, period);
+      P.d2[(size_t)(off + k) * TP_ROWS + lane] = plan_dist2<GEO>(P, o, q, period);
     }
   }
 }

@@ -7,6 +7,7 @@
 #include "decoder_tail.cuh"
 #include "decoder_tail_mma.cuh"
 #include "decoder_tail_plan.cuh"
+#include "encoder_plan.cuh"
 #include "dense_attention.cuh"
 #include "local_attention.cuh"
 #include "mlp_epilogue.cuh"
@@ -57,6 +58,9 @@ cudaError_t tail_plan_backward(int geo, const TallPlan& plan, const TailParams& 
 int wide_pad(int width);
 cudaError_t wide_forward(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
 cudaError_t wide_dscale(int geo, const WidePlan& w, const WideParams& P, cudaStream_t st);
+// tu_wide_plan.cu: the encoder walk over a cached (transposed) tile plan
+cudaError_t wide_plan_forward(int grid, const WideParams& P, const TailPlanDev& V, cudaStream_t st);
+cudaError_t wide_plan_dscale(int grid, const WideParams& P, const TailPlanDev& V, cudaStream_t st);
 // tu_loss.cu  (stage 0: partial sums, 1: finalize, 2: backward)
 cudaError_t rel_lp(int stage, const LossParams& P, int grid_x, cudaStream_t st);
 // tu_mlp_epilogue.cu

@@ -143,6 +143,8 @@ int check_stat(const pit_problem_t* p, const pit_rowstat_t* st, const float* per
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
+pit::TailPlanDev tail_plan_view(const pit_tail_plan_t* plan, int tiles_per_cta, int round);
+
 
 // ---------------------------------------------------------------------------------------------
 // "tall" kernels (shared meshes, M <= 1024, H <= 2): eligibility, launch shape, dispatch
@@ -260,6 +262,17 @@ WidePlan plan_wide(const pit_problem_t* p, const pit_rowstat_t* st) {
   w.grid = (int)((groups + per_cta - 1) / per_cta);
   w.ok = true;
   return w;
+}
+
+// Encoder-side ("columns") tile plan: usable when it describes this stage's column set
+bool column_plan_ok(const pit_problem_t* p, const pit_tail_plan_t* plan) {
+  return plan && plan->rec && plan->tile_off && plan->tile_cnt && plan->cand && plan->d2 && p->n_out <= pit::TALL_MAX_M &&
+         plan->n_tiles == (p->n_in + pit::TP_ROWS - 1) / pit::TP_ROWS;
+}
+int column_plan_grid(const pit_tail_plan_t* plan) {
+  const int want = (plan->n_tiles + pit::WP_WARPS - 1) / pit::WP_WARPS;   // one tile per warp ...
+  const int cap = sm_count() * 8;                                        // ... up to a full chip of resident CTAs
+  return want < cap ? want : cap;
 }
 
 pit::WideParams wide_params(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
@@ -495,7 +508,7 @@ TallPlan plan_tail_plan_fwd(const pit_problem_t* p, int out_dim, const pit_tail_
   TallPlan c{};
   if (!tail_plan_eligible(p, out_dim, plan)) return c;
   const int warps = p->batch < pit::TP_MAX_WARPS ? p->batch : pit::TP_MAX_WARPS;
-  c.l4 = warps < 8 ? warps : 8;  // tiles per round (kept in l4): 4 keeps three CTAs per SM at ~37 KB each and leaves most of the 228 KB to L1
+  c.l4 = warps < 4 ? warps : 4;  // tiles per round (kept in l4): 4 keeps three CTAs per SM at ~37 KB each and leaves most of the 228 KB to L1
   plan_tail_plan_grid(p, plan, c, pit::TP_FWD_CTAS, c.l4);
   c.smem = pit::tp_fwd_smem_bytes(p->n_head, p->n_in, p->dim, out_dim, c.l4);
   if (c.smem > (size_t)max_smem_optin() - 1024) return c;
@@ -636,7 +649,7 @@ int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh
 int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
                        const float* values, const float* scale, const pit_rowstat_t* stat, float* out, int64_t ld_out,
                        int64_t col_off, int32_t copy_values, float* rowsum, void* workspace, size_t workspace_bytes,
-                       void* stream) {
+                       const pit_tail_plan_t* column_plan, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (!mesh_out || !mesh_in || !values || !scale || !out || !rowsum) return fail(PIT_ERR_ARG, "null pointer");
   if (int rc = check_stat(p, stat, period)) return rc;
@@ -692,7 +705,10 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
     pit::WideParams W = wide_params(p, mesh_out, mesh_in, period, values, scale, stat);
     W.partial = P.partial;
     W.rowsum = rowsum;
-    PIT_CUDA(launch::wide_forward(geo_of(p), wide, W, st));
+    if (column_plan_ok(p, column_plan))
+      PIT_CUDA(launch::wide_plan_forward(column_plan_grid(column_plan), W, tail_plan_view(column_plan, 0, 0), st));
+    else
+      PIT_CUDA(launch::wide_forward(geo_of(p), wide, W, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const int64_t total = s.items * s.width;
     PIT_CUDA(launch::local_forward_finalize(total, P, st));
@@ -720,7 +736,7 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
 int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
                         const float* values, const float* scale, const pit_rowstat_t* stat, const float* rowsum,
                         const float* d_out, int64_t ld_out, int64_t col_off, int32_t accumulate_concat, float* d_values,
-                        float* d_scale, void* workspace, size_t workspace_bytes, void* stream) {
+                        float* d_scale, void* workspace, size_t workspace_bytes, const pit_tail_plan_t* column_plan, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (!mesh_out || !mesh_in || !values || !scale || !rowsum || !d_out) return fail(PIT_ERR_ARG, "null pointer");
   if (int rc = check_stat(p, stat, period)) return rc;
@@ -832,7 +848,10 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
       W.ld_out = ld_out;
       W.col_off = col_off;
       W.dscale_terms = P.dscale_terms;
-      PIT_CUDA(launch::wide_dscale(geo, wide, W, st));
+      if (column_plan_ok(p, column_plan))
+        PIT_CUDA(launch::wide_plan_dscale(column_plan_grid(column_plan), W, tail_plan_view(column_plan, 0, 0), st));
+      else
+        PIT_CUDA(launch::wide_dscale(geo, wide, W, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
       const dim3 grid((unsigned)((s.items + pit::WARPS_PER_BLOCK - 1) / pit::WARPS_PER_BLOCK), s.chunks, s.n_split);
@@ -961,63 +980,68 @@ int pit_bias_act_backward(const float* z, const float* bias, const float* d_out,
 }
 
 namespace {
-int check_tail_plan_args(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+int check_tail_plan_args(const pit_problem_t* p, int side, const float* mesh_out, const float* mesh_in, const float* period,
                          const pit_rowstat_t* stat, void* workspace, size_t workspace_bytes) {
   if (int rc = check_problem(p)) return rc;
   if (!mesh_out || !mesh_in || !workspace) return fail(PIT_ERR_ARG, "null pointer");
+  if (side != PIT_PLAN_ROWS && side != PIT_PLAN_COLUMNS) return fail(PIT_ERR_ARG, "tile plan: unknown side %d", side);
   if (int rc = check_stat(p, stat, period)) return rc;
-  if (p->mesh_batched || p->n_in > pit::TALL_MAX_M) return fail(PIT_ERR_ARG, "tail plan: needs shared meshes with M <= %d", pit::TALL_MAX_M);
-  const size_t need = launch::tail_plan_workspace_bytes(p->n_out);
+  const int small = side == PIT_PLAN_ROWS ? p->n_in : p->n_out;
+  if (p->mesh_batched || small > pit::TALL_MAX_M)
+    return fail(PIT_ERR_ARG, "tile plan: needs shared meshes with at most %d points on the candidate side", pit::TALL_MAX_M);
+  const size_t need = launch::tail_plan_workspace_bytes(side == PIT_PLAN_ROWS ? p->n_out : p->n_in);
   if (workspace_bytes < need) return fail(PIT_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
   return PIT_OK;
 }
 
-pit::PlanBuildParams plan_build_params(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+pit::PlanBuildParams plan_build_params(const pit_problem_t* p, int side, const float* mesh_out, const float* mesh_in, const float* period,
                                        const pit_rowstat_t* stat) {
   pit::PlanBuildParams B{};
-  B.mesh_out = mesh_out;
-  B.mesh_in = mesh_in;
+  B.transposed = side == PIT_PLAN_COLUMNS;
+  B.mesh_out = B.transposed ? mesh_in : mesh_out;   // tiled side
+  B.mesh_in = B.transposed ? mesh_out : mesh_in;    // candidate side
   B.period = p->variant == PIT_EUCLID ? nullptr : period;
   B.v_min = stat->v_min;
   B.v_lo = stat->v_lo;
   B.v_hi = stat->v_hi;
   B.masked = stat->masked;
-  B.N = p->n_out;
-  B.M = p->n_in;
+  B.N = B.transposed ? p->n_in : p->n_out;
+  B.M = B.transposed ? p->n_out : p->n_in;
   B.sd = p->space_dim;
-  B.n_tiles = (p->n_out + pit::TP_ROWS - 1) / pit::TP_ROWS;
+  B.n_tiles = (B.N + pit::TP_ROWS - 1) / pit::TP_ROWS;
   return B;
 }
 }  // namespace
 
-size_t pit_tail_plan_workspace_bytes(const pit_problem_t* p) {
+size_t pit_tail_plan_workspace_bytes(const pit_problem_t* p, int32_t side) {
   if (check_problem(p) != PIT_OK) return 0;
-  return launch::tail_plan_workspace_bytes(p->n_out);
+  return launch::tail_plan_workspace_bytes(side == PIT_PLAN_COLUMNS ? p->n_in : p->n_out);
 }
 
-int pit_tail_plan_rows(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+int pit_tail_plan_rows(const pit_problem_t* p, int32_t side, const float* mesh_out, const float* mesh_in, const float* period,
                        const pit_rowstat_t* stat, int32_t* tile_off, int32_t* tile_cnt, void* workspace, size_t workspace_bytes,
                        void* stream) {
-  if (int rc = check_tail_plan_args(p, mesh_out, mesh_in, period, stat, workspace, workspace_bytes)) return rc;
+  if (int rc = check_tail_plan_args(p, side, mesh_out, mesh_in, period, stat, workspace, workspace_bytes)) return rc;
   if (!tile_off || !tile_cnt) return fail(PIT_ERR_ARG, "null pointer");
-  PIT_CUDA(launch::tail_plan_rows(geo_of(p), cpl_of(p->n_in), plan_build_params(p, mesh_out, mesh_in, period, stat), tile_off, tile_cnt, workspace,
+  const pit::PlanBuildParams B0 = plan_build_params(p, side, mesh_out, mesh_in, period, stat);
+  PIT_CUDA(launch::tail_plan_rows(geo_of(p), cpl_of(B0.M), B0, tile_off, tile_cnt, workspace,
                                   static_cast<cudaStream_t>(stream)));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return PIT_OK;
 }
 
-int pit_tail_plan_fill(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+int pit_tail_plan_fill(const pit_problem_t* p, int32_t side, const float* mesh_out, const float* mesh_in, const float* period,
                        const pit_rowstat_t* stat, const int32_t* tile_off, void* rec, int16_t* cand, float* d2,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  if (int rc = check_tail_plan_args(p, mesh_out, mesh_in, period, stat, workspace, workspace_bytes)) return rc;
+  if (int rc = check_tail_plan_args(p, side, mesh_out, mesh_in, period, stat, workspace, workspace_bytes)) return rc;
   if (!tile_off || !rec || !cand || !d2) return fail(PIT_ERR_ARG, "null pointer");
   if (!aligned16(rec)) return fail(PIT_ERR_ARG, "tail plan: rec must be 16-byte aligned");
-  pit::PlanBuildParams B = plan_build_params(p, mesh_out, mesh_in, period, stat);
+  pit::PlanBuildParams B = plan_build_params(p, side, mesh_out, mesh_in, period, stat);
   B.tile_off = tile_off;
   B.rec = static_cast<float4*>(rec);
   B.cand = cand;
   B.d2 = d2;
-  PIT_CUDA(launch::tail_plan_fill(geo_of(p), cpl_of(p->n_in), B, workspace, static_cast<cudaStream_t>(stream)));
+  PIT_CUDA(launch::tail_plan_fill(geo_of(p), cpl_of(B.M), B, workspace, static_cast<cudaStream_t>(stream)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }

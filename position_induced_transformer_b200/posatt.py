@@ -140,11 +140,12 @@ class _MeshEntry:
     """What the cache keeps for one pair of shared meshes: contiguous copies, wrap period, row statistics and -- built on
     first use by a decoder -- the tile plan of the fused decoder tail."""
 
-    __slots__ = ("mesh_out", "mesh_in", "period", "stats", "tail_plan", "keep_alive")
+    __slots__ = ("mesh_out", "mesh_in", "period", "stats", "tail_plan", "column_plan", "keep_alive")
 
     def __init__(self, mesh_out, mesh_in, period, stats, keep_alive):
         self.mesh_out, self.mesh_in, self.period, self.stats = mesh_out, mesh_in, period, stats
-        self.tail_plan = None
+        self.tail_plan = None        # decoder side: tiles of mesh_out rows (built on first use by the fused decoder tail)
+        self.column_plan = None      # encoder side: tiles of mesh_in columns (built on first use by a wide masked stage)
         self.keep_alive = keep_alive
 
 
@@ -286,25 +287,26 @@ def use_tail_plan(enabled: bool) -> None:
     _TAIL_PLAN = bool(enabled)
 
 
-def build_tail_plan(st: _Stage, mesh_out, mesh_in, period, stats) -> TailPlan:
-    """Runs the two construction stages of the C ABI; one 4-byte device->host read in between sizes the candidate array."""
+def build_tail_plan(st: _Stage, mesh_out, mesh_in, period, stats, side: int = _cabi.PLAN_ROWS) -> TailPlan:
+    """Runs the two construction stages of the C ABI; one 4-byte device->host read in between sizes the candidate array.
+    side = PLAN_ROWS tiles the mesh_out rows (decoder stages), PLAN_COLUMNS the mesh_in columns (local encoder stages)."""
     v_min, v_lo, v_hi, w, masked = stats
     rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
     dev = st.device
     with torch.cuda.device(dev):
-        n_tiles = (st.N + 31) // 32
-        ws_bytes = int(_cabi.lib.pit_tail_plan_workspace_bytes(C.byref(st.problem)))
+        n_tiles = ((st.N if side == _cabi.PLAN_ROWS else st.M) + 31) // 32
+        ws_bytes = int(_cabi.lib.pit_tail_plan_workspace_bytes(C.byref(st.problem), side))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         tile_off = torch.empty(n_tiles + 1, dtype=torch.int32, device=dev)
         tile_cnt = torch.empty(n_tiles, dtype=torch.int32, device=dev)
-        _cabi.check(_cabi.lib.pit_tail_plan_rows(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), C.byref(rs),
+        _cabi.check(_cabi.lib.pit_tail_plan_rows(C.byref(st.problem), side, mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), C.byref(rs),
                                                  tile_off.data_ptr(), tile_cnt.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev)),
                     "pit_tail_plan_rows")
         total = int(tile_off[-1].item())
         rec = torch.empty((n_tiles * 32, 4), dtype=torch.float32, device=dev)
         cand = torch.empty(max(total, 1), dtype=torch.int16, device=dev)
         d2 = torch.empty((max(total, 1), 32), dtype=torch.float32, device=dev)
-        _cabi.check(_cabi.lib.pit_tail_plan_fill(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), C.byref(rs),
+        _cabi.check(_cabi.lib.pit_tail_plan_fill(C.byref(st.problem), side, mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), C.byref(rs),
                                                  tile_off.data_ptr(), rec.data_ptr(), cand.data_ptr(), d2.data_ptr(), ws.data_ptr(),
                                                  ws_bytes, _stream(dev)), "pit_tail_plan_fill")
     return TailPlan(rec, tile_off, tile_cnt, cand, d2)
@@ -327,6 +329,17 @@ def _rowstat_struct(v_min, v_lo, v_hi, w: float, masked: bool) -> _cabi.RowStat:
                          w, int(masked))
 
 
+def column_plan_for(entry: Optional[_MeshEntry], st: _Stage, masked: bool) -> Optional[TailPlan]:
+    """The cached encoder-side plan of a shared-mesh stage with few rows and a huge column set (the conditions under which
+    the C ABI takes the wide path: masked, H <= 2, B*D <= 32, M >= 4096 and M >= 8 N), built on first use."""
+    if (not _TAIL_PLAN or entry is None or st.batched or not masked or st.H > 2 or st.B * st.D > 32 or st.N > 1024
+            or st.M < 4096 or st.M < 8 * st.N or st.B * st.M * st.D >= 2 ** 31):
+        return None
+    if entry.column_plan is None and not torch.cuda.is_current_stream_capturing():
+        entry.column_plan = build_tail_plan(st, entry.mesh_out, entry.mesh_in, entry.period, entry.stats, _cabi.PLAN_COLUMNS)
+    return entry.column_plan
+
+
 class _PositionAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, values, scale, mesh_out, mesh_in, n_head, locality, variant, self_concat):
@@ -334,8 +347,9 @@ class _PositionAttention(torch.autograd.Function):
         _require(values.is_cuda, f"values must be a CUDA tensor (position-attention has no CPU path), got {values.device}")
         scale_shape = scale.shape
         scale = scale.reshape(-1).contiguous()
-        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked), _entry = prepare_meshes(
+        mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked), entry = prepare_meshes(
             mesh_out, mesh_in, values, n_head, variant, float(locality))
+        plan = None if self_concat else column_plan_for(entry, st, masked)
         _check_tensor("scale", scale, st.device)
         _require(scale.numel() == st.H, f"scale must have n_head={st.H} entries, got {scale.numel()}")
         if self_concat:
@@ -352,10 +366,11 @@ class _PositionAttention(torch.autograd.Function):
                 _cabi.check(_cabi.lib.pit_posatt_forward(
                     C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
                     scale.data_ptr(), C.byref(rs), out.data_ptr(), width, col_off, int(self_concat), rowsum.data_ptr(),
-                    ws.data_ptr(), ws_bytes, _stream(st.device)), "pit_posatt_forward")
+                    ws.data_ptr(), ws_bytes, C.byref(plan.struct) if plan is not None else None, _stream(st.device)), "pit_posatt_forward")
         ctx.save_for_backward(values, scale, mesh_out, mesh_in, period if period is not None else scale.new_empty(0),
                               v_min, v_lo, v_hi, rowsum)
         ctx.meta = (n_head, variant, self_concat, w, masked, scale_shape)
+        ctx.plan = plan          # keeps the plan's tensors alive until the backward has run
         return out
 
     @staticmethod
@@ -382,8 +397,8 @@ class _PositionAttention(torch.autograd.Function):
                     _cabi.check(_cabi.lib.pit_posatt_backward(
                         C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
                         scale.data_ptr(), C.byref(rs), rowsum.data_ptr(), d_out.data_ptr(), width, col_off,
-                        int(self_concat), _ptr(d_values), _ptr(d_scale), ws.data_ptr(), ws_bytes, _stream(st.device)),
-                        "pit_posatt_backward")
+                        int(self_concat), _ptr(d_values), _ptr(d_scale), ws.data_ptr(), ws_bytes,
+                        C.byref(ctx.plan.struct) if ctx.plan is not None else None, _stream(st.device)), "pit_posatt_backward")
         if need_scale:
             d_scale = d_scale.reshape(scale_shape)
         return d_values, d_scale, None, None, None, None, None, None

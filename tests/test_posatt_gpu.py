@@ -162,7 +162,41 @@ def test_softmax_rows_reproduce_constants(cuda_device):
     assert rel_linf(got, want) <= FWD_TOL
 
 
-def test_darcy421_encoder_full_size(cuda_device):
+@pytest.fixture(params=[True, False], ids=["tile_plan", "scan"])
+def column_plan(request):
+    """Run a wide (encoder) stage with the cached column plan and with the per-launch row walk."""
+    from position_induced_transformer_b200 import posatt
+    posatt.use_tail_plan(request.param)
+    posatt.mesh_cache.clear()
+    yield request.param
+    posatt.use_tail_plan(True)
+
+
+@pytest.mark.parametrize("variant,q", [("euclid", 0.05), ("euclid", 0.004), ("periodic2d", 0.02)])
+def test_wide_encoder_irregular_mesh(variant, q, column_plan, cuda_device):
+    """Few rows, thousands of columns, narrow values: the local-encoder kernels on a mesh without any coherence."""
+    gen = torch.Generator().manual_seed(31)
+    if variant == "periodic2d":
+        ax = np.linspace(0, 1, 81)[:-1]
+        mi = torch.tensor(np.vstack([m.ravel() for m in np.meshgrid(ax, ax)]).T, dtype=torch.float)
+        ax = np.linspace(0, 1, 7)[:-1]
+        mo = torch.tensor(np.vstack([m.ravel() for m in np.meshgrid(ax, ax)]).T, dtype=torch.float)
+    else:
+        mo, mi = torch.rand(50, 2, generator=gen), torch.rand(5000, 2, generator=gen)
+    vals = torch.randn(3, mi.shape[0], 5, generator=gen)
+    scale = torch.tensor([0.8, 4.0])
+    s_cpu = scale.clone().reshape(-1, 1, 1).requires_grad_(True)
+    want = po.dense_contract(po.dense_attention(mo, mi, s_cpu, q, variant), vals)
+    up = torch.randn(want.shape, generator=gen)
+    want.backward(up)
+    s_gpu = scale.to(cuda_device).requires_grad_(True)
+    got = _pa()(mo.to(cuda_device), mi.to(cuda_device), vals.to(cuda_device), s_gpu, q, variant)
+    got.backward(up.to(cuda_device))
+    assert rel_linf(got.detach().cpu(), want.detach()) <= FWD_TOL
+    assert rel_linf(s_gpu.grad.cpu().reshape(-1), s_cpu.grad.reshape(-1)) <= GRAD_TOL
+
+
+def test_darcy421_encoder_full_size(column_plan, cuda_device):
     """Encoder stage at BASELINE size (256 x 177241, split along the columns) against the oracle."""
     ax = np.linspace(0, 1, 421)
     mesh = torch.tensor(np.vstack([m.ravel() for m in np.meshgrid(ax, ax)]).T, dtype=torch.float)
