@@ -108,6 +108,22 @@ def shared_mesh_forward(model, mesh_in, func_in, mesh_out):
     return model.decoder(model.mesh_ltt, h, mo).reshape(f.shape[0], *lead, model.out_dim)
 
 
+def vorticity_forward(model, mesh_in, func_in, mesh_out):
+    """train_vorticity.py:44-62: the shared-mesh wrapper with a parameter-free InstanceNorm1d over the latent points after the
+    encoder and after the processor."""
+    sd = model.space_dim
+    lead = mesh_out.shape[:-1]
+    norm = torch.nn.InstanceNorm1d(model.hid_dim)
+    mi, mo = mesh_in.reshape(-1, sd), mesh_out.reshape(-1, sd)
+    f = func_in.reshape(func_in.shape[0], -1, model.in_dim)
+    f = torch.cat((torch.tile(mi.unsqueeze(0), [f.shape[0], 1, 1]), f), -1)
+    h = model.encoder(mi, f, model.mesh_ltt)
+    h = norm(h.permute(0, 2, 1)).permute(0, 2, 1)
+    h = model.processor(h, model.mesh_ltt)
+    h = norm(h.permute(0, 2, 1)).permute(0, 2, 1)
+    return model.decoder(model.mesh_ltt, h, mo).reshape(f.shape[0], *lead, model.out_dim)
+
+
 def cloud_forward(model, mesh_in, func_in, mesh_ltt, mesh_out):
     h = model.encoder(mesh_in, func_in, mesh_ltt)
     h = model.processor(h, mesh_ltt)
@@ -181,6 +197,10 @@ def main():
     model_case(ref, "vorticity", "pit_periodic2d",
                dict(space_dim=2, in_dim=1, out_dim=1, hid_dim=16, n_head=2, n_blocks=1, mesh_ltt=p8, en_loc=0.05, de_loc=0.1),
                shared_mesh_forward, (p32, rn(2, 1024, 1), p32), rn(2, 1024, 1), 2)
+    # the script's own wrapper (instance norms around the processor), 10 input frames as train_vorticity.py:76
+    model_case(ref, "vorticity_norm", "pit_periodic2d",
+               dict(space_dim=2, in_dim=10, out_dim=1, hid_dim=16, n_head=2, n_blocks=1, mesh_ltt=p8, en_loc=0.05, de_loc=0.1),
+               vorticity_forward, (p32, rn(2, 1024, 10), p32), rn(2, 1024, 1), 2)
 
 
 if __name__ == "__main__":

@@ -49,16 +49,23 @@ def n_blocks_of(p: Params) -> int:
     return 1 + max(int(k.split(".")[1]) for k in p if k.startswith("conv."))
 
 
-def forward_shared_mesh(p: Params, variant, mesh_in, func_in, mesh_ltt, mesh_out, en_loc, de_loc):
+def _instance_norm(x: torch.Tensor) -> torch.Tensor:
+    """nn.InstanceNorm1d(hid) applied to (B, L, hid) through the permutes of train_vorticity.py:56, 59."""
+    return F.instance_norm(x.permute(0, 2, 1)).permute(0, 2, 1)
+
+
+def forward_shared_mesh(p: Params, variant, mesh_in, func_in, mesh_ltt, mesh_out, en_loc, de_loc, instance_norm=False):
     """Burgers / Sod / Darcy style forward (train_burgers.py:40-49, train_darcy.py:46-59):
-    the batch shares one mesh; coordinates are prepended to the input features."""
+    the batch shares one mesh; coordinates are prepended to the input features.  `instance_norm`: the vorticity script's
+    normalisation of the latent features after the encoder and after the processor (train_vorticity.py:44-62)."""
     sd = mesh_ltt.shape[-1]
     lead = mesh_out.shape[:-1]
     mesh_in, mesh_out = mesh_in.reshape(-1, sd), mesh_out.reshape(-1, sd)
     func_in = func_in.reshape(func_in.shape[0], mesh_in.shape[0], -1)
     feats = torch.cat((mesh_in.unsqueeze(0).expand(func_in.shape[0], -1, -1), func_in), -1)
-    h = encode(p, variant, mesh_in, feats, mesh_ltt, en_loc)
-    h = process(p, variant, h, mesh_ltt, n_blocks_of(p))
+    norm = _instance_norm if instance_norm else (lambda x: x)
+    h = norm(encode(p, variant, mesh_in, feats, mesh_ltt, en_loc))
+    h = norm(process(p, variant, h, mesh_ltt, n_blocks_of(p)))
     out = decode(p, variant, mesh_ltt, h, mesh_out, de_loc)
     return out.reshape(func_in.shape[0], *lead, -1)
 
@@ -109,11 +116,6 @@ def init_params(spec, seed: int = 0) -> Params:
     return p
 
 
-def _instance_norm(x: torch.Tensor) -> torch.Tensor:
-    """nn.InstanceNorm1d(hid) applied to (B, L, hid) through the permutes of train_vorticity.py:56, 59."""
-    return F.instance_norm(x.permute(0, 2, 1)).permute(0, 2, 1)
-
-
 def forward_spec(p: Params, spec, inputs):
     """One model application for a spec: the `forward` its script defines."""
     _, _, _, _, _, _, en_loc, de_loc = spec.ctor
@@ -126,16 +128,7 @@ def forward_spec(p: Params, spec, inputs):
             return forward_point_cloud(p, mesh_in, func_in, ltt, mesh_out.reshape(b, -1, 2), en_loc, de_loc).reshape(*lead, -1)
         return forward_point_cloud(p, mesh_in, func_in, mesh_out, mesh_out, en_loc, de_loc)
     mesh, ltt = spec.mesh, spec.mesh_ltt.reshape(-1, spec.mesh_ltt.shape[-1])
-    if spec.extra.get("instance_norm"):                  # train_vorticity.py:44-62
-        sd = ltt.shape[-1]
-        lead = mesh.shape[:-1]
-        m = mesh.reshape(-1, sd)
-        func_in = inputs[0].reshape(inputs[0].shape[0], m.shape[0], -1)
-        feats = torch.cat((m.unsqueeze(0).expand(func_in.shape[0], -1, -1), func_in), -1)
-        h = _instance_norm(encode(p, spec.variant, m, feats, ltt, en_loc))
-        h = _instance_norm(process(p, spec.variant, h, ltt, n_blocks_of(p)))
-        return decode(p, spec.variant, ltt, h, m, de_loc).reshape(func_in.shape[0], *lead, -1)
-    out = forward_shared_mesh(p, spec.variant, mesh, inputs[0], ltt, mesh, en_loc, de_loc)
+    out = forward_shared_mesh(p, spec.variant, mesh, inputs[0], ltt, mesh, en_loc, de_loc, bool(spec.extra.get("instance_norm")))
     return out + inputs[0] if spec.extra.get("residual") else out     # train_cylinder.py:52
 
 

@@ -8,10 +8,13 @@
 // into tiles of 32; a tile lists its candidate rows (~6 at Darcy-421: the encoder keeps 2 % of 177 241 columns per row, i.e.
 // every column is seen by ~5 rows) and the bit-exact squared distances of its 32 columns to each of them.
 //
-//   wide_plan_fwd_kernel     lane = column: its value row (B*D <= 32 scalars) in registers, one weight per candidate row and
-//                            head from the cached d2 (exact per-head cut as everywhere), the 32 lanes' contributions combined
-//                            with a reduce-scatter butterfly and added to partial[(row, h), :] / rowsum[h, row] with REDs
-//   wide_plan_dscale_kernel  the three per-(row, head) sums of the scale gradient (see wide_dscale_kernel) from the same walk
+// Per tile the work is a small dense product, run on mma.sync.m16n8k8 (3xTF32, fp32 accumulate) by one warp:
+//   wide_plan_fwd_kernel     out^T[e x (row, h)] += U^T[e x 32 columns] . P[32 columns x (row, h)]   (e = the B*D <= 32 value
+//                            scalars of a column): the weights are evaluated directly in B-fragment order from the cached d2
+//                            (exact per-head cut as everywhere), 8 candidate rows x 2 heads per group; the accumulators go to
+//                            partial[(row, h), :] with REDs, the row sums to rowsum[h, row]
+//   wide_plan_dscale_kernel  dP[32 columns x (row, h)] = U . dO[row, h, :]^T the same way, then the three per-(row, head) sums
+//                            of the scale gradient (see wide_dscale_kernel) from the accumulator fragments
 // The generic finalize kernels of local_attention.cuh turn the sums into the output / the gradient, as for the wide kernels.
 #pragma once
 #include "decoder_tail_plan.cuh"
@@ -40,52 +43,111 @@ __device__ __forceinline__ void wp_build_rows(const WideParams& P, float* rowtab
   }
 }
 
+// Weight of (tile column c, candidate k) for head h; rowc = {top, cut} of the candidate's row.
+__device__ __forceinline__ float wp_weight(float d2, float s, float top, float cut, bool live) {
+  if (!live) return 0.f;
+  const float sc = __fmul_rn(d2, s);
+  return sc <= cut ? expf(__fsub_rn(top, sc)) : 0.f;
+}
+
 template <int NH, int WPAD>
 __global__ void __launch_bounds__(WP_THREADS) wide_plan_fwd_kernel(const WideParams P, const TailPlanDev V) {
+  constexpr int MT = (WPAD + 15) / 16;  // m16 tiles over the value scalars
   extern __shared__ __align__(16) unsigned char wide_smem_raw[];
   float* rowtab = reinterpret_cast<float*>(wide_smem_raw);
   int* val_off = reinterpret_cast<int*>(rowtab + (size_t)P.N * 2 * NH);
   wp_build_rows<NH>(P, rowtab, val_off);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   float s[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
   for (int tile = blockIdx.x * WP_WARPS + warp; tile < V.n_tiles; tile += gridDim.x * WP_WARPS) {
     const int off = __ldg(V.tile_off + tile), cnt = __ldg(V.tile_cnt + tile);
-    const int j = __float_as_int(__ldg(V.rec + (size_t)tile * TP_ROWS + lane).w);  // this lane's column (-1: padding)
-    float u[WPAD];
+    const int jc = __float_as_int(__ldg(V.rec + (size_t)tile * TP_ROWS + lane).w);  // column of tile slot `lane` (-1: padding)
+    // A = U^T: a[ks][mt] = {U[col 8ks+t][e], U[col 8ks+t][e+8], U[col 8ks+t+4][e], U[col 8ks+t+4][e+8]}, e = 16mt + g
+    float a[4][MT][4];
+    bool clive[4][2];
 #pragma unroll
-    for (int e = 0; e < WPAD; ++e) u[e] = (e < P.width && j >= 0) ? __ldg(P.values + val_off[e] + (int64_t)j * P.D) : 0.f;
-    for (int k = 0; k < cnt; ++k) {
-      const int r = (int)__ldg(V.cand + off + k);
-      const float d2 = __ldg(V.d2 + (size_t)(off + k) * TP_ROWS + lane);
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int j = __shfl_sync(FULL, jc, 8 * ks + t + 4 * half);
+        clive[ks][half] = j >= 0;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int up = 0; up < 2; ++up) {
+            const int e = 16 * mt + g + 8 * up;
+            a[ks][mt][2 * half + up] = (j >= 0 && e < P.width) ? __ldg(P.values + val_off[e] + (int64_t)j * P.D) : 0.f;
+          }
+      }
+    }
+    for (int cg = 0; cg < cnt; cg += 8) {  // groups of 8 candidate rows: n = candidate cg + g
+      const bool klive = cg + g < cnt;
+      const int r = klive ? (int)__ldg(V.cand + off + cg + g) : 0;
+      float top[NH], cut[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) top[h] = rowtab[(size_t)r * 2 * NH + 2 * h], cut[h] = rowtab[(size_t)r * 2 * NH + 2 * h + 1];
+      float acc[MT][NH][4], lsum[NH];
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
-        float p = 0.f;
-        if (j >= 0) {
-          const float sc = __fmul_rn(d2, s[h]);
-          if (sc <= rowtab[(size_t)r * 2 * NH + 2 * h + 1]) p = expf(__fsub_rn(rowtab[(size_t)r * 2 * NH + 2 * h], sc));
-        }
-        const float lsum = warp_sum(p);
-        if (lsum > 0.f) {  // warp-uniform
-          // lane e ends up with element e of the tile's contribution: a reduce-scatter butterfly (31 shuffles) instead of one
-          // full warp reduction per element
-          float v[32];
+        lsum[h] = 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = e < WPAD ? p * u[e] : 0.f;
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const bool upper = (lane & o) != 0;
+          for (int i = 0; i < 4; ++i) acc[mt][h][i] = 0.f;
+      }
 #pragma unroll
-            for (int i = 0; i < o; ++i) {
-              const float keep = upper ? v[i + o] : v[i], send = upper ? v[i] : v[i + o];
-              v[i] = keep + __shfl_xor_sync(FULL, send, o);
-            }
+      for (int ks = 0; ks < 4; ++ks) {
+        // B = P: b = {P[col 8ks+t][cand], P[col 8ks+t+4][cand]} per head
+        float d2[2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) d2[half] = klive ? __ldg(V.d2 + (size_t)(off + cg + g) * TP_ROWS + 8 * ks + t + 4 * half) : 0.f;
+        uint32_t al[MT][4], ah[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ah[mt][i] = __float_as_uint(a[ks][mt][i]), al[mt][i] = tm_trunc_lo(a[ks][mt][i]);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float p0 = wp_weight(d2[0], s[h], top[h], cut[h], klive && clive[ks][0]);
+          const float p1 = wp_weight(d2[1], s[h], top[h], cut[h], klive && clive[ks][1]);
+          lsum[h] += p0 + p1;
+          const float h0 = tm_round_hi(p0), h1 = tm_round_hi(p1);
+          const uint32_t bh[2] = {__float_as_uint(h0), __float_as_uint(h1)}, bl[2] = {__float_as_uint(p0 - h0), __float_as_uint(p1 - h1)};
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_tf32_16x8x8(acc[mt][h], al[mt], bh);
+            mma_tf32_16x8x8(acc[mt][h], ah[mt], bl);
+            mma_tf32_16x8x8(acc[mt][h], ah[mt], bh);
           }
-          if (lane < P.width) atomicAdd(P.partial + ((int64_t)r * NH + h) * P.width + lane, v[0]);
-          if (lane == 0) atomicAdd(P.rowsum + (int64_t)h * P.N + r, lsum);
         }
+      }
+      // row sums: this lane covered 8 of the 32 columns of candidate g; the other 24 sit in the lanes sharing g
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        lsum[h] += __shfl_xor_sync(FULL, lsum[h], 1);
+        lsum[h] += __shfl_xor_sync(FULL, lsum[h], 2);
+        if (t == 0 && klive && lsum[h] > 0.f) atomicAdd(P.rowsum + (int64_t)h * P.N + r, lsum[h]);
+      }
+      // accumulators: value scalar e = 16mt + g (+8), candidate cg + 2t (+1)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int k = cg + 2 * t + q;
+        if (k >= cnt) continue;
+        const int rk = (int)__ldg(V.cand + off + k);
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int up = 0; up < 2; ++up) {
+              const int e = 16 * mt + g + 8 * up;
+              const float v = acc[mt][h][2 * up + q];
+              if (e < P.width && v != 0.f) atomicAdd(P.partial + ((int64_t)rk * NH + h) * P.width + e, v);
+            }
       }
     }
   }
@@ -93,6 +155,7 @@ __global__ void __launch_bounds__(WP_THREADS) wide_plan_fwd_kernel(const WidePar
 
 template <int NH, int WPAD>
 __global__ void __launch_bounds__(WP_THREADS) wide_plan_dscale_kernel(const WideParams P, const TailPlanDev V) {
+  constexpr int KS = (WPAD + 7) / 8;  // k-steps over the value scalars
   extern __shared__ __align__(16) unsigned char wide_smem_raw[];
   float* rowtab = reinterpret_cast<float*>(wide_smem_raw);
   int* val_off = reinterpret_cast<int*>(rowtab + (size_t)P.N * 2 * NH);
@@ -101,11 +164,11 @@ __global__ void __launch_bounds__(WP_THREADS) wide_plan_dscale_kernel(const Wide
   for (int rh = threadIdx.x; rh < P.N * NH; rh += WP_THREADS) {
     const int r = rh / NH, h = rh - r * NH;
     const float* src = P.d_out + (int64_t)r * P.ld_out + P.col_off + (int64_t)h * P.D;
-    float* g = gtab + (size_t)rh * WPAD;
+    float* gr = gtab + (size_t)rh * WPAD;
     int b = 0, d = 0;
 #pragma unroll
     for (int e = 0; e < WPAD; ++e) {
-      g[e] = e < P.width ? __ldg(src + (int64_t)b * P.N * P.ld_out + d) : 0.f;
+      gr[e] = e < P.width ? __ldg(src + (int64_t)b * P.N * P.ld_out + d) : 0.f;
       if (++d == P.D) {
         d = 0;
         ++b;
@@ -114,38 +177,96 @@ __global__ void __launch_bounds__(WP_THREADS) wide_plan_dscale_kernel(const Wide
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   float s[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) s[h] = __ldg(P.scale + h);
   for (int tile = blockIdx.x * WP_WARPS + warp; tile < V.n_tiles; tile += gridDim.x * WP_WARPS) {
     const int off = __ldg(V.tile_off + tile), cnt = __ldg(V.tile_cnt + tile);
-    const int j = __float_as_int(__ldg(V.rec + (size_t)tile * TP_ROWS + lane).w);
-    float u[WPAD];
+    const int jc = __float_as_int(__ldg(V.rec + (size_t)tile * TP_ROWS + lane).w);
+    // A = U: a[mt][ks] = {U[col 16mt+g][e], U[col 16mt+g+8][e], U[col 16mt+g][e+4], U[col 16mt+g+8][e+4]}, e = 8ks + t
+    float a[2][KS][4];
+    bool clive[2][2];
 #pragma unroll
-    for (int e = 0; e < WPAD; ++e) u[e] = (e < P.width && j >= 0) ? __ldg(P.values + val_off[e] + (int64_t)j * P.D) : 0.f;
-    for (int k = 0; k < cnt; ++k) {
-      const int r = (int)__ldg(V.cand + off + k);
-      const float d2 = __ldg(V.d2 + (size_t)(off + k) * TP_ROWS + lane);
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        float p = 0.f;
-        if (j >= 0) {
-          const float sc = __fmul_rn(d2, s[h]);
-          if (sc <= rowtab[(size_t)r * 2 * NH + 2 * h + 1]) p = expf(__fsub_rn(rowtab[(size_t)r * 2 * NH + 2 * h], sc));
+      for (int up = 0; up < 2; ++up) {
+        const int j = __shfl_sync(FULL, jc, 16 * mt + g + 8 * up);
+        clive[mt][up] = j >= 0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int e = 8 * ks + t + 4 * half;
+            a[mt][ks][2 * half + up] = (j >= 0 && e < P.width) ? __ldg(P.values + val_off[e] + (int64_t)j * P.D) : 0.f;
+          }
+      }
+    for (int cg = 0; cg < cnt; cg += 8) {
+      // B = dO^T: n = candidate cg + g; b = {G[row][h][8ks+t], G[row][h][8ks+t+4]}
+      const bool nlive = cg + g < cnt;
+      const int rn = nlive ? (int)__ldg(V.cand + off + cg + g) : 0;
+      float dp[2][NH][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dp[mt][h][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t al[2][4], ah[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ah[mt][i] = __float_as_uint(a[mt][ks][i]), al[mt][i] = tm_trunc_lo(a[mt][ks][i]);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float* gr = gtab + ((size_t)rn * NH + h) * WPAD + 8 * ks + t;
+          const float g0 = (nlive && 8 * ks + t < WPAD) ? gr[0] : 0.f, g1 = (nlive && 8 * ks + t + 4 < WPAD) ? gr[4] : 0.f;
+          const float h0 = tm_round_hi(g0), h1 = tm_round_hi(g1);
+          const uint32_t bh[2] = {__float_as_uint(h0), __float_as_uint(h1)}, bl[2] = {__float_as_uint(g0 - h0), __float_as_uint(g1 - h1)};
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma_tf32_16x8x8(dp[mt][h], al[mt], bh);
+            mma_tf32_16x8x8(dp[mt][h], ah[mt], bl);
+            mma_tf32_16x8x8(dp[mt][h], ah[mt], bh);
+          }
         }
-        if (!__any_sync(FULL, p > 0.f)) continue;
-        const float* g = gtab + ((size_t)r * NH + h) * WPAD;
-        float dp = 0.f;  // <dO[row,h,:], U[j,:]>
+      }
+      // dp[mt][h][2*up + q]: column 16mt + g + 8up, candidate cg + 2t + q.  Weights in the same layout, then the three sums.
 #pragma unroll
-        for (int e = 0; e < WPAD; ++e) dp = fmaf(g[e], u[e], dp);
-        const float pd = p * d2;
-        const float a_sum = warp_sum(pd * dp), b_sum = warp_sum(p * dp), m_sum = warp_sum(pd);
-        if (lane == 0) {
-          float* dst = P.dscale_terms + ((int64_t)r * NH + h) * 3;
-          atomicAdd(dst + 0, a_sum);
-          atomicAdd(dst + 1, b_sum);
-          atomicAdd(dst + 2, m_sum);
-        }
+      for (int q = 0; q < 2; ++q) {
+        const int k = cg + 2 * t + q;
+        const bool klive = k < cnt;
+        const int rk = klive ? (int)__ldg(V.cand + off + k) : 0;
+        float sums[NH][3];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) sums[h][0] = sums[h][1] = sums[h][2] = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int up = 0; up < 2; ++up) {
+            const bool live = klive && clive[mt][up];
+            const float d2 = live ? __ldg(V.d2 + (size_t)(off + k) * TP_ROWS + 16 * mt + g + 8 * up) : 0.f;
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              const float p = wp_weight(d2, s[h], rowtab[(size_t)rk * 2 * NH + 2 * h], rowtab[(size_t)rk * 2 * NH + 2 * h + 1], live);
+              const float pd = p * d2, dpv = dp[mt][h][2 * up + q];
+              sums[h][0] = fmaf(pd, dpv, sums[h][0]);
+              sums[h][1] = fmaf(p, dpv, sums[h][1]);
+              sums[h][2] += pd;
+            }
+          }
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            float v = sums[h][i];
+            v += __shfl_xor_sync(FULL, v, 4);
+            v += __shfl_xor_sync(FULL, v, 8);
+            v += __shfl_xor_sync(FULL, v, 16);
+            if (g == 0 && klive && v != 0.f) atomicAdd(P.dscale_terms + ((int64_t)rk * NH + h) * 3 + i, v);
+          }
       }
     }
   }

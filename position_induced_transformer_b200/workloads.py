@@ -45,6 +45,10 @@ class DarcyPiT(SharedMeshPiT, P.pit_fixed):
     pass
 
 
+class Periodic2dPiT(SharedMeshPiT, P.pit_periodic2d):
+    pass
+
+
 class VorticityPiT(P.pit_periodic2d):
     """Periodic 2-D vorticity model with an instance norm after the encoder and after the processor
     (train_vorticity.py:43, 56-59)."""

@@ -9,7 +9,7 @@ from conftest import golden_names, load_golden, rel_linf, t
 pytestmark = pytest.mark.gpu
 
 MODEL_CLASS = {"burgers": "BurgersPiT", "sod": "SodPiT", "darcy43": "DarcyPiT", "elasticity": "ElasticityPiT",
-               "naca": "NacaPiT", "vorticity": "VorticityPiT"}
+               "naca": "NacaPiT", "vorticity": "Periodic2dPiT", "vorticity_norm": "VorticityPiT"}
 
 
 @pytest.mark.parametrize("name", golden_names("model_"))

@@ -75,7 +75,7 @@ def test_model_oracle_matches_reference(name):
     else:
         sd = int(g["ctor/space_dim"])
         out = pit_oracle.forward_shared_mesh(params, variant_of(cls), ins[0], ins[1], t(g["ctor/mesh_ltt"]).reshape(-1, sd),
-                                             ins[2], en_loc, de_loc)
+                                             ins[2], en_loc, de_loc, instance_norm=name.endswith("_norm"))
     assert torch.equal(out.detach(), t(g["out"]))
     loss = pit_oracle.rel_lp_loss(t(g["target"]), out, int(g["ctor/out_dim"]), int(g["loss_p"]))
     assert torch.equal(loss.detach(), t(g["loss"]))
