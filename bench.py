@@ -525,6 +525,21 @@ def measure_workload(name, args, rank, world, dev, detail, tf32_peak, hbm_peak):
                         "tensor_frac": flops / t_s / 1e12 / tf32_peak, "plan_ksteps": ksteps,
                         "unfused_equivalent": {"bytes": unfused_bytes(k), "GBps": unfused_bytes(k) / t_s / 1e9,
                                                "frac": unfused_bytes(k) / t_s / 1e9 / hbm_peak}})
+        elif k[0].startswith("processor"):
+            # the fused processor (csrc/processor_block.cuh): k[9] carries the number of blocks.  Per block the attention products are
+            # 2 H N N B D flop forward (C = P X) and twice that backward (dP and the value gradient), issued as 3xTF32; the Linear
+            # products 2 B N D ((1+H) D + D) flop forward and twice that backward, issued as the matmul precision says.
+            # Bytes: block inputs and the saved C / Z1 / Z2 (written forward, read backward), dC through the L2 scratch, in / out.
+            _, _, _, B, H, N, _, D, _, nb = k
+            bwd = k[0] == "processor_bwd"
+            att = 2.0 * H * N * N * B * D * nb * (2 if bwd else 1)
+            lin = 2.0 * B * N * D * ((1 + H) * D + D) * nb * (2 if bwd else 1)
+            lin_terms = 3 if args.precision == "highest" else 1
+            nbytes = 4 * B * N * (2 * D + nb * (H * D + 3 * D) + (2 * nb * H * D if bwd else 0))
+            row.update({"concat": True, "n_blocks": nb, "bytes": nbytes, "hbm_frac": nbytes / t_s / 1e9 / hbm_peak,
+                        "dense_flops": att, "linear_flops": lin, "posatt_tflops": att / t_s / 1e12,
+                        "posatt_tflops_issued": 3 * att / t_s / 1e12, "tf32_flops_issued": 3 * att + lin_terms * lin,
+                        "tensor_frac": (3 * att + lin_terms * lin) / t_s / 1e12 / tf32_peak})
         else:
             nbytes = unfused_bytes(k)
             row.update({"bytes": nbytes, "hbm_frac": nbytes / t_s / 1e9 / hbm_peak})

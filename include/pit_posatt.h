@@ -14,6 +14,7 @@
  *   pit_rel_lp*             the training loss RelLpNorm           utils.py:60-98
  *   pit_decoder_tail*       pit.decoder = up + de MLP, fused      pit.py:124-127, 21-26
  *   pit_tail_plan*          lambda-independent part of the mask   pit.py:136 (re-sorted every step there)
+ *   pit_processor*          pit.processor, all blocks, fused      pit.py:114-122, 37-44, 21-26
  *
  * Conventions
  *   - all tensors are fp32, contiguous, row-major, resident on the CURRENT CUDA device;
@@ -34,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 5
+#define PIT_ABI_VERSION 6
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -210,6 +211,38 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
                               int32_t out_dim, const float* rowsum, const float* d_out, float* d_y,
                               float* d_scale, float* d_b1, float* d_w2, float* d_b2, const pit_tail_plan_t* plan,
                               void* stream);
+
+/* Fused processor: pit.processor (pit.py:114-122) for a shared latent mesh -- n_blocks x [ self position-attention with
+ * locality 1 and concat (pit.py:37-44) + kaiming_mlp (pit.py:21-26) + GELU (pit.py:121) ] -- as ONE launch per direction.
+ * problem: mesh_batched = 0, n_out = n_in = N latent points (a multiple of 32, at most 256), dim = hidden width D (32 or 64),
+ * n_head <= 2; n_blocks <= 8.  One thread-block cluster per sample; nothing N x N is written to memory.
+ *   mesh   [N,sd]           period: device scalar (periodic variants) or NULL
+ *   x0     [B,N,D]          input of the first block
+ *   scale  [n_blocks,H]     tan(c*(1+sin(lmda))) of every block's attention layer (pit_head_scale_forward)
+ *   blocks host array of n_blocks entries: mlp1.weight [D,(1+H)D], mlp1.bias [D], mlp2.weight [D,D], mlp2.bias [D] (device)
+ *   linear_3xtf32  != 0: the Linear products run as 3xTF32 (fp32 parity, torch 'highest'); 0: single TF32 products, what torch
+ *                  runs them as under set_float32_matmul_precision('high') (pit.py:2).  Attention products are always 3xTF32.
+ *   saved  pit_processor_saved_floats() floats, written by the forward and consumed by the backward (opaque)
+ *   out    [B,N,D]          output of the last block
+ * Backward: d_out [B,N,D] -> d_x0 [B,N,D]; `grads` (pit_processor_grad_floats() floats, overwritten) receives per block
+ * d_mlp1.weight [D,(1+H)D] | d_mlp1.bias [D] | d_mlp2.weight [D,D] | d_mlp2.bias [D], and after the last block d_scale
+ * [n_blocks,H]; scratch: pit_processor_scratch_floats() floats. */
+typedef struct pit_processor_block {
+  const float* w1;
+  const float* b1;
+  const float* w2;
+  const float* b2;
+} pit_processor_block_t;
+int pit_processor_supported(const pit_problem_t* p, int32_t n_blocks);
+size_t pit_processor_saved_floats(const pit_problem_t* p, int32_t n_blocks);
+size_t pit_processor_grad_floats(const pit_problem_t* p, int32_t n_blocks);
+size_t pit_processor_scratch_floats(const pit_problem_t* p);
+int pit_processor_forward(const pit_problem_t* p, int32_t n_blocks, const float* mesh, const float* period, const float* x0,
+                          const float* scale, const pit_processor_block_t* blocks, int32_t linear_3xtf32, float* saved, float* out,
+                          void* stream);
+int pit_processor_backward(const pit_problem_t* p, int32_t n_blocks, const float* mesh, const float* period, const float* x0,
+                           const float* scale, const pit_processor_block_t* blocks, int32_t linear_3xtf32, const float* saved,
+                           const float* d_out, float* d_x0, float* grads, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

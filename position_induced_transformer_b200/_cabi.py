@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 5
+ABI_VERSION = 6
 PLAN_ROWS, PLAN_COLUMNS = 0, 1
 
 EXPORTS = (
@@ -24,6 +24,8 @@ EXPORTS = (
     "pit_head_scale_forward", "pit_head_scale_backward",
     "pit_bias_act_supported", "pit_bias_act_forward", "pit_bias_act_backward",
     "pit_rel_lp_supported", "pit_rel_lp_forward", "pit_rel_lp_backward",
+    "pit_processor_supported", "pit_processor_saved_floats", "pit_processor_grad_floats", "pit_processor_scratch_floats",
+    "pit_processor_forward", "pit_processor_backward",
 )
 
 
@@ -40,6 +42,10 @@ class RowStat(C.Structure):
 class TailPlan(C.Structure):
     _fields_ = [("rec", C.c_void_p), ("tile_off", C.c_void_p), ("tile_cnt", C.c_void_p), ("cand", C.c_void_p), ("d2", C.c_void_p),
                 ("n_tiles", C.c_int32)]
+
+
+class ProcessorBlock(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p)]
 
 
 def _load() -> C.CDLL:
@@ -78,6 +84,15 @@ def _load() -> C.CDLL:
     lib.pit_rel_lp_supported.argtypes = [i32, i64, i32, i32]
     lib.pit_rel_lp_forward.argtypes = [f32p, f32p, i32, i64, i32, i32, f32p, f32p, p]
     lib.pit_rel_lp_backward.argtypes = [f32p, f32p, f32p, f32p, i32, i64, i32, i32, f32p, p]
+    lib.pit_processor_supported.argtypes = [C.POINTER(Problem), i32]
+    for name in ("pit_processor_saved_floats", "pit_processor_grad_floats"):
+        getattr(lib, name).argtypes = [C.POINTER(Problem), i32]
+        getattr(lib, name).restype = C.c_size_t
+    lib.pit_processor_scratch_floats.argtypes = [C.POINTER(Problem)]
+    lib.pit_processor_scratch_floats.restype = C.c_size_t
+    lib.pit_processor_forward.argtypes = [C.POINTER(Problem), i32, f32p, f32p, f32p, f32p, C.POINTER(ProcessorBlock), i32, f32p, f32p, p]
+    lib.pit_processor_backward.argtypes = [C.POINTER(Problem), i32, f32p, f32p, f32p, f32p, C.POINTER(ProcessorBlock), i32, f32p,
+                                           f32p, f32p, f32p, f32p, p]
     if lib.pit_abi_version() != ABI_VERSION:
         raise ImportError(f"libpit_posatt.so ABI {lib.pit_abi_version()} != expected {ABI_VERSION}; rebuild it")
     return lib

@@ -11,6 +11,7 @@
 #include "dense_attention.cuh"
 #include "local_attention.cuh"
 #include "mlp_epilogue.cuh"
+#include "processor_block.cuh"
 #include "rel_lp_loss.cuh"
 #include "rowstat.cuh"
 #include "tall_attention.cuh"
@@ -69,6 +70,11 @@ cudaError_t bias_act(bool backward, const EpiParams& P, int grid, cudaStream_t s
 cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cudaStream_t st);
 // both gradient modes of a small stage (64-column tiles) in one launch
 cudaError_t dense_bwd_pair(int geo, const DenseParams& Ps, dim3 gs, const DenseParams& Pv, dim3 gv, cudaStream_t st);
+
+// tu_processor.cu: the whole processor (n_blocks x [self attention + concat + MLP + GELU]) in one cluster launch per direction
+constexpr int PROC_TILE_ROWS = 32;  // latent rows per CTA; the cluster of a sample has N / 32 <= 8 CTAs
+size_t processor_smem_bytes(int D, int H, int N);
+cudaError_t processor(bool backward, int D, int H, bool lin3, const ProcParams& P, cudaStream_t st);
 
 }  // namespace launch
 }  // namespace pit

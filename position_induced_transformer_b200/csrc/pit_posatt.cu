@@ -1126,4 +1126,111 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   return PIT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// fused processor (pit.py:114-122)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+bool processor_eligible(const pit_problem_t* p, int32_t n_blocks) {
+  const int tr = launch::PROC_TILE_ROWS;
+  if (p->mesh_batched || p->n_out != p->n_in) return false;
+  if (n_blocks < 1 || n_blocks > pit::PB_MAX_BLOCKS) return false;
+  if (p->n_head < 1 || p->n_head > 2 || (p->dim != 32 && p->dim != 64)) return false;
+  if (p->n_out % tr != 0 || p->n_out / tr < 1 || p->n_out / tr > 8) return false;   // portable cluster size
+  if (p->batch < 1 || p->batch > 65535) return false;
+  return launch::processor_smem_bytes(p->dim, p->n_head, p->n_out) <= (size_t)max_smem_optin();
+}
+
+pit::ProcParams processor_params(const pit_problem_t* p, int32_t n_blocks, const float* mesh, const float* period, const float* x0,
+                                 const float* scale, const pit_processor_block_t* blocks, float* saved) {
+  pit::ProcParams P = {};
+  P.geo = geo_of(p);
+  P.sd = p->space_dim;
+  P.B = p->batch;
+  P.N = p->n_out;
+  P.n_blocks = n_blocks;
+  P.mesh = mesh;
+  P.period = period;
+  P.x0 = x0;
+  P.scale = scale;
+  P.saved = saved;
+  for (int k = 0; k < n_blocks; ++k) P.w[k] = pit::ProcWeights{blocks[k].w1, blocks[k].b1, blocks[k].w2, blocks[k].b2};
+  return P;
+}
+
+int check_processor(const pit_problem_t* p, int32_t n_blocks, const float* mesh, const float* period, const float* x0, const float* scale,
+                    const pit_processor_block_t* blocks, const float* saved) {
+  if (int rc = check_problem(p)) return rc;
+  if (!processor_eligible(p, n_blocks)) return fail(PIT_ERR_ARG, "processor: unsupported configuration (see pit_processor_supported)");
+  if (!mesh || !x0 || !scale || !blocks || !saved) return fail(PIT_ERR_ARG, "null pointer");
+  if (p->variant != PIT_EUCLID && !period) return fail(PIT_ERR_ARG, "periodic variant needs the wrap length");
+  if (!aligned16(x0) || !aligned16(saved)) return fail(PIT_ERR_ARG, "processor: x0 and saved must be 16-byte aligned");
+  for (int k = 0; k < n_blocks; ++k) {
+    if (!blocks[k].w1 || !blocks[k].b1 || !blocks[k].w2 || !blocks[k].b2) return fail(PIT_ERR_ARG, "processor: null weight pointer");
+    if ((reinterpret_cast<uintptr_t>(blocks[k].b1) | reinterpret_cast<uintptr_t>(blocks[k].b2)) & 7u)
+      return fail(PIT_ERR_ARG, "processor: biases must be 8-byte aligned");
+  }
+  return PIT_OK;
+}
+}  // namespace
+
+int pit_processor_supported(const pit_problem_t* p, int32_t n_blocks) {
+  if (check_problem(p) != PIT_OK) return 0;
+  return processor_eligible(p, n_blocks) ? 1 : 0;
+}
+
+size_t pit_processor_saved_floats(const pit_problem_t* p, int32_t n_blocks) {
+  if (check_problem(p) != PIT_OK || n_blocks < 1) return 0;
+  return (size_t)pit::proc_saved_layout(p->batch, p->n_out, p->n_head, p->dim).stride * (size_t)n_blocks;
+}
+
+size_t pit_processor_grad_floats(const pit_problem_t* p, int32_t n_blocks) {
+  if (check_problem(p) != PIT_OK || n_blocks < 1) return 0;
+  const size_t d = (size_t)p->dim, cw = d * (1 + (size_t)p->n_head);
+  return (size_t)n_blocks * (d * cw + d + d * d + d + (size_t)p->n_head);
+}
+
+size_t pit_processor_scratch_floats(const pit_problem_t* p) {
+  if (check_problem(p) != PIT_OK) return 0;
+  return 2 * (size_t)p->batch * p->n_out * p->n_head * p->dim;
+}
+
+int pit_processor_forward(const pit_problem_t* p, int32_t n_blocks, const float* mesh, const float* period, const float* x0,
+                          const float* scale, const pit_processor_block_t* blocks, int32_t linear_3xtf32, float* saved, float* out,
+                          void* stream) {
+  if (int rc = check_processor(p, n_blocks, mesh, period, x0, scale, blocks, saved)) return rc;
+  if (!out) return fail(PIT_ERR_ARG, "null pointer");
+  pit::ProcParams P = processor_params(p, n_blocks, mesh, period, x0, scale, blocks, saved);
+  P.out = out;
+  PIT_CUDA(launch::processor(false, p->dim, p->n_head, linear_3xtf32 != 0, P, static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
+int pit_processor_backward(const pit_problem_t* p, int32_t n_blocks, const float* mesh, const float* period, const float* x0,
+                           const float* scale, const pit_processor_block_t* blocks, int32_t linear_3xtf32, const float* saved,
+                           const float* d_out, float* d_x0, float* grads, float* scratch, void* stream) {
+  if (int rc = check_processor(p, n_blocks, mesh, period, x0, scale, blocks, saved)) return rc;
+  if (!d_out || !d_x0 || !grads || !scratch) return fail(PIT_ERR_ARG, "null pointer");
+  if (!aligned16(scratch) || (reinterpret_cast<uintptr_t>(grads) & 7u) || (reinterpret_cast<uintptr_t>(d_x0) & 7u))
+    return fail(PIT_ERR_ARG, "processor: scratch must be 16-byte, grads and d_x0 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pit::ProcParams P = processor_params(p, n_blocks, mesh, period, x0, scale, blocks, const_cast<float*>(saved));
+  P.d_out = d_out;
+  P.d_x0 = d_x0;
+  P.scratch = scratch;
+  const size_t d = (size_t)p->dim, cw = d * (1 + (size_t)p->n_head);
+  float* q = grads;
+  for (int k = 0; k < n_blocks; ++k) {
+    P.g[k].d_w1 = q, q += d * cw;
+    P.g[k].d_b1 = q, q += d;
+    P.g[k].d_w2 = q, q += d * d;
+    P.g[k].d_b2 = q, q += d;
+  }
+  P.d_scale = q;
+  PIT_CUDA(cudaMemsetAsync(grads, 0, pit_processor_grad_floats(p, n_blocks) * sizeof(float), st));
+  PIT_CUDA(launch::processor(true, p->dim, p->n_head, linear_3xtf32 != 0, P, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
 }  // extern "C"

@@ -24,10 +24,12 @@ from torch.nn.functional import gelu
 np.random.seed(0)
 from math import pi
 
-from .posatt import bias_act, bias_act_supported, decoder_tail, decoder_tail_supported, head_scale_cuda, position_attention
+from .posatt import (bias_act, bias_act_supported, decoder_tail, decoder_tail_supported, head_scale_cuda, position_attention,
+                     processor_blocks, processor_supported)
 
 __all__ = [
     "torch", "nn", "gelu", "np", "pi", "kaiming_mlp", "use_host_scale_map", "use_fused_decoder_tail", "use_fused_mlp_epilogue",
+    "use_fused_processor",
     "posatt", "posatt_cross", "pit",
     "posatt_fixed", "posatt_cross_fixed", "pit_fixed",
     "posatt_periodic1d", "posatt_cross_periodic1d", "pit_periodic1d",
@@ -182,6 +184,16 @@ class posatt_cross_periodic2d(posatt_periodic2d):
     _cross = True
 
 
+_FUSABLE_SELF = (posatt_fixed, posatt_periodic1d, posatt_periodic2d)
+_FUSED_PROCESSOR = True
+
+
+def use_fused_processor(enabled: bool) -> None:
+    """Switch the fused processor (all blocks in one launch per direction) on or off; off runs attention and MLP per block."""
+    global _FUSED_PROCESSOR
+    _FUSED_PROCESSOR = bool(enabled)
+
+
 _FUSABLE_CROSS = (posatt_cross_fixed, posatt_cross_periodic1d, posatt_cross_periodic2d)
 _FUSED_DECODER_TAIL = True
 
@@ -236,7 +248,26 @@ class pit(nn.Module):
     def encoder(self, mesh_in, func_in, mesh_ltt):
         return self._mlp_gelu(self.en_layer, self.down(mesh_ltt, mesh_in, func_in))
 
+    def _fusable_processor(self, func_ltt, mesh_ltt):
+        """Stock layers on a shared latent mesh, shapes the fused kernel covers (anything customised runs block by block)."""
+        if not (_FUSED_PROCESSOR and len(self.conv) == len(self.mlp) > 0 and torch.is_tensor(mesh_ltt) and mesh_ltt.dim() == 2
+                and torch.is_tensor(func_ltt) and func_ltt.is_cuda and func_ltt.dim() == 3):
+            return False
+        kind, hid, h = type(self.conv[0]), func_ltt.shape[-1], self.conv[0].n_head
+        for attend, mix in zip(self.conv, self.mlp):
+            if type(attend) is not kind or kind not in _FUSABLE_SELF or attend.n_head != h or attend.locality < 1.0:
+                return False
+            if (type(mix) is not kaiming_mlp or type(mix.mlp1) is not nn.Linear or type(mix.mlp2) is not nn.Linear
+                    or mix.mlp1.bias is None or mix.mlp2.bias is None or tuple(mix.mlp1.weight.shape) != (hid, (1 + h) * hid)
+                    or tuple(mix.mlp2.weight.shape) != (hid, hid) or mix.mlp1.weight.dtype != torch.float32):
+                return False
+        return processor_supported(mesh_ltt, func_ltt, h, len(self.conv), kind._variant)
+
     def processor(self, func_ltt, mesh_ltt):
+        if self._fusable_processor(func_ltt, mesh_ltt):
+            scales = head_scale(torch.stack([attend.lmda.reshape(-1) for attend in self.conv]))
+            weights = [w for mix in self.mlp for w in (mix.mlp1.weight, mix.mlp1.bias, mix.mlp2.weight, mix.mlp2.bias)]
+            return processor_blocks(func_ltt, mesh_ltt, scales, self.conv[0].n_head, self.conv[0]._variant, weights)
         for attend, mix in zip(self.conv, self.mlp):
             func_ltt = self._mlp_gelu(mix, attend(mesh_ltt, func_ltt))
         return func_ltt

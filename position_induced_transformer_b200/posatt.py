@@ -498,6 +498,87 @@ def bias_act(z: torch.Tensor, bias: torch.Tensor, apply_gelu: bool) -> torch.Ten
 
 
 # ----------------------------------------------------------------------------------------------
+# fused processor (pit.py:114-122): every block of a shared-mesh model in one launch per direction
+# ----------------------------------------------------------------------------------------------
+def _processor_problem(mesh: torch.Tensor, x: torch.Tensor, n_head: int, variant: str) -> _cabi.Problem:
+    return _cabi.Problem(_cabi.VARIANT_CODE[variant], mesh.shape[-1], 0, x.shape[0], int(n_head), mesh.shape[0], mesh.shape[0], x.shape[-1])
+
+
+def _linear_3xtf32() -> int:
+    """torch's matmul precision decides how the Linear products run: 'highest' -> 3xTF32 (fp32 parity), else single TF32
+    products -- what cuBLAS runs nn.Linear as under 'high' (pit.py:2)."""
+    return int(torch.get_float32_matmul_precision() == "highest")
+
+
+class _Processor(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, mesh, period, scales, n_head, variant, *weights):
+        x0 = x0.contiguous()
+        n_blocks = len(weights) // 4
+        weights = tuple(w.contiguous() for w in weights)
+        scales = scales.contiguous()
+        prob = _processor_problem(mesh, x0, n_head, variant)
+        blocks = (_cabi.ProcessorBlock * n_blocks)(*[_cabi.ProcessorBlock(*(w.data_ptr() for w in weights[4 * k:4 * k + 4]))
+                                                     for k in range(n_blocks)])
+        lin3 = _linear_3xtf32()
+        saved = torch.empty(int(_cabi.lib.pit_processor_saved_floats(C.byref(prob), n_blocks)), dtype=torch.float32, device=x0.device)
+        out = torch.empty_like(x0)
+        key = _Stage.__new__(_Stage)
+        key.variant, key.batched, key.B, key.H, key.N, key.M, key.D, key.sd, key.device = (
+            variant, False, x0.shape[0], int(n_head), mesh.shape[0], mesh.shape[0], x0.shape[-1], mesh.shape[-1], x0.device)
+        with torch.cuda.device(x0.device), _timed("processor_fwd", key, n_blocks):
+            _cabi.check(_cabi.lib.pit_processor_forward(C.byref(prob), n_blocks, mesh.data_ptr(), _ptr(period), x0.data_ptr(),
+                                                        scales.data_ptr(), blocks, lin3, saved.data_ptr(), out.data_ptr(),
+                                                        _stream(x0.device)), "pit_processor_forward")
+        ctx.save_for_backward(x0, mesh, scales, saved, *weights)
+        ctx.period, ctx.prob, ctx.lin3, ctx.key, ctx.n_blocks = period, prob, lin3, key, n_blocks
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x0, mesh, scales, saved, *weights = ctx.saved_tensors
+        n_blocks, prob = ctx.n_blocks, ctx.prob
+        d_out = d_out.contiguous()
+        blocks = (_cabi.ProcessorBlock * n_blocks)(*[_cabi.ProcessorBlock(*(w.data_ptr() for w in weights[4 * k:4 * k + 4]))
+                                                     for k in range(n_blocks)])
+        grads = torch.empty(int(_cabi.lib.pit_processor_grad_floats(C.byref(prob), n_blocks)), dtype=torch.float32, device=x0.device)
+        scratch = torch.empty(int(_cabi.lib.pit_processor_scratch_floats(C.byref(prob))), dtype=torch.float32, device=x0.device)
+        d_x0 = torch.empty_like(x0)
+        with torch.cuda.device(x0.device), _timed("processor_bwd", ctx.key, n_blocks):
+            _cabi.check(_cabi.lib.pit_processor_backward(C.byref(prob), n_blocks, mesh.data_ptr(), _ptr(ctx.period), x0.data_ptr(),
+                                                         scales.data_ptr(), blocks, ctx.lin3, saved.data_ptr(), d_out.data_ptr(),
+                                                         d_x0.data_ptr(), grads.data_ptr(), scratch.data_ptr(), _stream(x0.device)),
+                        "pit_processor_backward")
+        outs, off = [], 0
+        for w in weights:
+            outs.append(grads[off:off + w.numel()].view(w.shape))
+            off += w.numel()
+        d_scales = grads[off:off + scales.numel()].view(scales.shape)
+        return (d_x0, None, None, d_scales, None, None, *outs)
+
+
+@torch.compiler.disable
+def processor_supported(mesh: torch.Tensor, x: torch.Tensor, n_head: int, n_blocks: int, variant: str) -> bool:
+    """True when the fused processor covers this case: a shared latent mesh of 32..256 points (a multiple of 32), float32 CUDA
+    features of width 32 or 64, at most two heads and eight blocks."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and mesh.dim() == 2 and mesh.is_cuda and mesh.dtype == torch.float32
+            and mesh.shape[0] == x.shape[1] and mesh.shape[-1] in (1, 2) and variant in _VARIANTS and x.numel() > 0):
+        return False
+    if torch.is_grad_enabled() and mesh.requires_grad:
+        return False
+    return bool(_cabi.lib.pit_processor_supported(C.byref(_processor_problem(mesh, x, n_head, variant)), int(n_blocks)))
+
+
+@torch.compiler.disable
+def processor_blocks(x: torch.Tensor, mesh: torch.Tensor, scales: torch.Tensor, n_head: int, variant: str, weights) -> torch.Tensor:
+    """for k: x = gelu(mlp_k(cat(x, A_k x)))  with A_k the global position-attention of block k on the shared mesh `mesh`
+    (pit.py:114-122).  scales [n_blocks, H] = head scales of the blocks; weights = (mlp1.weight, mlp1.bias, mlp2.weight, mlp2.bias)
+    per block, flattened.  Gradients flow to x, scales and every weight."""
+    mesh, _, _, period, _, _ = prepare_meshes(mesh, mesh, x, n_head, variant, 1.0)   # cached contiguous copy and wrap length
+    return _Processor.apply(x, mesh, period, scales, int(n_head), variant, *weights)
+
+
+# ----------------------------------------------------------------------------------------------
 # relative Lp loss (utils.py:60-98): partial sums + finalize forward, one elementwise pass backward
 # ----------------------------------------------------------------------------------------------
 class _RelLp(torch.autograd.Function):
