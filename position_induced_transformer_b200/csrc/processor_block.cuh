@@ -209,17 +209,16 @@ __device__ __forceinline__ PbB<NT> pb_b_cols(const float* base, int ldb) {
   return b;
 }
 
-// Warp-level product on mma.sync.m16n8k8: acc[mt][nt] += A[16 mt + ., k] B[k, 8 nt + .] over `ksteps` (a multiple of 4) steps
+// Warp-level product on mma.sync.m16n8k8: acc[mt][nt] += A[16 mt + ., k] B[k, 8 nt + .] over `ksteps` (a multiple of PB_CHAIN) steps
 // of 8.  A_SK / B_SK: compile-time distance (floats) between consecutive k of the operand, so every load of a chain of four
 // k-steps has an immediate offset.  B_LDG: operand B lives in global memory (weights), read through the read-only path.
 // X3: hi*hi + lo*hi + hi*lo (pb_split); otherwise one product on operands rounded to the nearest TF32.
 // Accumulator fragment: acc[..][0] = (row g, col 2t), [1] = (g, 2t+1), [2] = (g+8, 2t), [3] = (g+8, 2t+1).
-template <int MT, int NT, bool X3, int A_SK, int B_SK, bool B_LDG = false>
+template <int MT, int NT, bool X3, int A_SK, int B_SK, bool B_LDG = false, int PB_CHAIN = 4>
 __device__ __forceinline__ void pb_gemm(float (&acc)[MT][NT][4], int ksteps, PbA<MT> a, PbB<NT> b) {
   // The tensor pipe accumulates with truncation: a chain of 3 x 32 accumulating MMAs drifts by a few 1e-6 (relative, biased).
   // The 3xTF32 products therefore run in chains of four k-steps from zero and are added to `acc` by the fp32 pipe
   // (round to nearest), as Ootomo & Yokota do for their error-corrected TF32 GEMM.
-  constexpr int PB_CHAIN = 4;
   for (int kc = 0; kc < ksteps; kc += PB_CHAIN) {
     float part[MT][NT][4];
     if (X3) {
@@ -304,6 +303,7 @@ struct ProcShape {
   static constexpr int ITEMS_LIN = (MTR / MT_LIN) * (D / 8);
   // weight-gradient products [D x TR] [TR x cols]
   static constexpr int MT_W = D >= 64 ? 2 : 1, NT_W = D >= 64 ? 2 : 1;
+  static constexpr int CHAIN_W = TR / 8 >= 4 ? 4 : TR / 8;   // their reduction runs over the TR rows only
   static_assert(TR % 16 == 0 && D % 16 == 0 && PB_THREADS % D == 0, "unsupported tile shape");
   static_assert(ITEMS_LIN <= PB_WARPS, "the backward keeps one Linear-shaped item per warp in registers");
 };
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) processor_bwd_kernel(const Proc
       const int m0 = mg * S::MT_W * 16, n0 = ng * S::NT_W * 8;
       float acc[S::MT_W][S::NT_W][4];
       pb_zero(acc);
-      pb_gemm<S::MT_W, S::NT_W, LIN3, LDD, LDD>(acc, TR / 8, pb_a_cols<S::MT_W>(AB + m0, LDD), pb_b_rows<S::NT_W>(H1 + n0, LDD));
+      pb_gemm<S::MT_W, S::NT_W, LIN3, LDD, LDD, false, S::CHAIN_W>(acc, TR / 8, pb_a_cols<S::MT_W>(AB + m0, LDD), pb_b_rows<S::NT_W>(H1 + n0, LDD));
 #pragma unroll
       for (int mt = 0; mt < S::MT_W; ++mt)
 #pragma unroll
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) processor_bwd_kernel(const Proc
       const int m0 = mg * S::MT_W * 16, n0 = ng * S::NT_W * 8;
       float acc[S::MT_W][S::NT_W][4];
       pb_zero(acc);
-      pb_gemm<S::MT_W, S::NT_W, LIN3, LDD, LDC>(acc, TR / 8, pb_a_cols<S::MT_W>(AB + m0, LDD), pb_b_rows<S::NT_W>(CAT + n0, LDC));
+      pb_gemm<S::MT_W, S::NT_W, LIN3, LDD, LDC, false, S::CHAIN_W>(acc, TR / 8, pb_a_cols<S::MT_W>(AB + m0, LDD), pb_b_rows<S::NT_W>(CAT + n0, LDC));
 #pragma unroll
       for (int mt = 0; mt < S::MT_W; ++mt)
 #pragma unroll
