@@ -9,6 +9,7 @@
  *   pit_rowstat             the row sort inside torch.quantile    pit.py:49, 136, 197, 255
  *   pit_posatt_forward      dist2att + convolution (+ concat)     pit.py:46-57, 133-144, 190-200, 247-258, 37-44
  *   pit_posatt_backward     what autograd replays for the above   (no explicit code in the reference)
+ *   pit_posatt_backward_coords  ... with respect to the meshes    pit.py:47, 134, 191-195, 248-253 (dist2att is differentiable in them)
  *   pit_head_scale*         the scale map tan(c*(1+sin(lmda)))    pit.py:48, 135, 196, 254
  *   pit_bias_act*           bias + GELU epilogues of the MLPs     pit.py:21-26, 111, 121
  *   pit_rel_lp*             the training loss RelLpNorm           utils.py:60-98
@@ -35,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 6
+#define PIT_ABI_VERSION 7
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -129,6 +130,17 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
                         int64_t ld_out, int64_t col_off, int32_t accumulate_concat,
                         float* d_values, float* d_scale, void* workspace, size_t workspace_bytes,
                         const pit_tail_plan_t* column_plan, void* stream);
+
+/* Gradient with respect to the mesh coordinates (`dX`): what autograd gives the reference when a mesh requires grad (no script
+ * does; a learnable latent mesh would).  Same inputs as pit_posatt_backward; outputs, all overwritten:
+ *   d_mesh_out [(B),N,sd], d_mesh_in [(B),M,sd]   (summed over the batch for shared meshes; the two may NOT alias)
+ *   d_period   [1]  gradient with respect to the wrap length l of the periodic variants (NULL for PIT_EUCLID); l is a function
+ *              of mesh_in (pit.py:191-192, 248-250) and the caller chains d_period through that expression.
+ * No gradient flows through the quantile mask, as in the reference.  A correctness path: one warp per (sample, row). */
+int pit_posatt_backward_coords(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                               const float* values, const float* scale, const pit_rowstat_t* stat, const float* rowsum,
+                               const float* d_out, int64_t ld_out, int64_t col_off, float* d_mesh_out, float* d_mesh_in,
+                               float* d_period, void* stream);
 
 /* Per-head scale map of pit.py:48:  scale[i] = tan(c * (1 + sin(lmda[i]))),  c = fp32(0.25*pi*(1-1e-7)),
  * each operation rounded to fp32 separately as the reference's chain of torch ops does (sin, add, mul, tan:

@@ -13,12 +13,12 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 6
+ABI_VERSION = 7
 PLAN_ROWS, PLAN_COLUMNS = 0, 1
 
 EXPORTS = (
     "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
-    "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward",
+    "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward", "pit_posatt_backward_coords",
     "pit_decoder_tail_supported", "pit_decoder_tail_forward", "pit_decoder_tail_backward",
     "pit_tail_plan_workspace_bytes", "pit_tail_plan_rows", "pit_tail_plan_fill",
     "pit_head_scale_forward", "pit_head_scale_backward",
@@ -66,6 +66,8 @@ def _load() -> C.CDLL:
                                        f32p, i64, i64, i32, f32p, p, C.c_size_t, C.POINTER(TailPlan), p]
     lib.pit_posatt_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat), f32p,
                                         f32p, i64, i64, i32, f32p, f32p, p, C.c_size_t, C.POINTER(TailPlan), p]
+    lib.pit_posatt_backward_coords.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat), f32p,
+                                               f32p, i64, i64, f32p, f32p, f32p, p]
     lib.pit_decoder_tail_supported.argtypes = [C.POINTER(Problem), i32]
     lib.pit_decoder_tail_forward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
                                              f32p, f32p, f32p, i32, f32p, f32p, C.POINTER(TailPlan), p]

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "coord_gradient.cuh"
 #include "decoder_tail.cuh"
 #include "decoder_tail_mma.cuh"
 #include "decoder_tail_plan.cuh"
@@ -71,6 +72,8 @@ cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cu
 // both gradient modes of a small stage (64-column tiles) in one launch
 cudaError_t dense_bwd_pair(int geo, const DenseParams& Ps, dim3 gs, const DenseParams& Pv, dim3 gv, cudaStream_t st);
 
+// tu_coord_gradient.cu: gradient with respect to the mesh coordinates
+cudaError_t coord_gradient(int geo, const CoordGradParams& P, cudaStream_t st);
 // tu_processor.cu: the whole processor (n_blocks x [self attention + concat + MLP + GELU]) in one cluster launch per direction
 constexpr int PROC_TILE_ROWS = 32;  // latent rows per CTA; the cluster of a sample has N / 32 <= 8 CTAs
 size_t processor_smem_bytes(int D, int H, int N);

@@ -1233,4 +1233,33 @@ int pit_processor_backward(const pit_problem_t* p, int32_t n_blocks, const float
   return PIT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// coordinate gradients
+// ---------------------------------------------------------------------------------------------------------------------
+int pit_posatt_backward_coords(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                               const float* values, const float* scale, const pit_rowstat_t* stat, const float* rowsum,
+                               const float* d_out, int64_t ld_out, int64_t col_off, float* d_mesh_out, float* d_mesh_in,
+                               float* d_period, void* stream) {
+  if (int rc = check_problem(p)) return rc;
+  if (!mesh_out || !mesh_in || !values || !scale || !rowsum || !d_out || !d_mesh_out || !d_mesh_in) return fail(PIT_ERR_ARG, "null pointer");
+  if (int rc = check_stat(p, stat, period)) return rc;
+  if (p->variant != PIT_EUCLID && !d_period) return fail(PIT_ERR_ARG, "periodic variant: d_period is required");
+  if ((int64_t)p->batch * p->n_out > (int64_t)2147483647 * pit::CG_WARPS) return fail(PIT_ERR_ARG, "too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pit::CoordGradParams P = {};
+  P.mesh_out = mesh_out, P.mesh_in = mesh_in, P.period = period, P.values = values, P.scale = scale;
+  P.v_min = stat->v_min, P.v_lo = stat->v_lo, P.v_hi = stat->v_hi, P.rowsum = rowsum, P.d_out = d_out;
+  P.weight = stat->weight, P.masked = stat->masked;
+  P.B = p->batch, P.H = p->n_head, P.N = p->n_out, P.M = p->n_in, P.D = p->dim, P.sd = p->space_dim, P.mesh_batched = p->mesh_batched;
+  P.ld_out = ld_out, P.col_off = col_off;
+  P.d_mesh_out = d_mesh_out, P.d_mesh_in = d_mesh_in, P.d_period = p->variant == PIT_EUCLID ? nullptr : d_period;
+  const size_t copies = p->mesh_batched ? (size_t)p->batch : 1;
+  PIT_CUDA(cudaMemsetAsync(d_mesh_out, 0, copies * p->n_out * p->space_dim * sizeof(float), st));
+  if (d_mesh_in != d_mesh_out) PIT_CUDA(cudaMemsetAsync(d_mesh_in, 0, copies * p->n_in * p->space_dim * sizeof(float), st));
+  if (d_period) PIT_CUDA(cudaMemsetAsync(d_period, 0, sizeof(float), st));
+  PIT_CUDA(launch::coord_gradient(geo_of(p), P, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
 }  // extern "C"

@@ -24,8 +24,8 @@ from torch.nn.functional import gelu
 np.random.seed(0)
 from math import pi
 
-from .posatt import (bias_act, bias_act_supported, decoder_tail, decoder_tail_supported, head_scale_cuda, position_attention,
-                     processor_blocks, processor_supported)
+from .posatt import (bias_act, bias_act_supported, decoder_tail, decoder_tail_supported, head_scale_cuda, meshes_need_grad,
+                     position_attention, processor_blocks, processor_supported)
 
 __all__ = [
     "torch", "nn", "gelu", "np", "pi", "kaiming_mlp", "use_host_scale_map", "use_fused_decoder_tail", "use_fused_mlp_epilogue",
@@ -277,6 +277,7 @@ class pit(nn.Module):
         # Fused tail: attention + both Linears + GELU in one kernel, nothing N x (H*D) wide is written to memory.
         # Only taken for the stock layer types on a shared mesh; anything customised runs the two modules as written.
         if (_FUSED_DECODER_TAIL and type(up) in _FUSABLE_CROSS and type(de) is kaiming_mlp and mesh_ltt.dim() == 2
+                and not meshes_need_grad(mesh_out, mesh_ltt)
                 and func_ltt.is_cuda and func_ltt.dim() == 3 and de.mlp1.in_features == up.n_head * func_ltt.shape[-1]
                 and decoder_tail_supported(mesh_ltt, func_ltt, up.n_head, de.mlp1.out_features, de.mlp2.out_features)):
             return decoder_tail(mesh_out, mesh_ltt, func_ltt, head_scale(up.lmda), up.locality, de.mlp1.weight, de.mlp1.bias,

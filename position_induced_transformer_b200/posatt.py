@@ -10,8 +10,9 @@ self stage, the ``torch.cat`` of pit.py:44.  Nothing of size N x M is materialis
 the kernels never depend on a tracing compiler.
 
 Autograd: gradients flow to ``values`` and to the per-head ``scale`` (and from there to
-``lmda`` through ordinary torch ops); meshes are constants, as at every call site of the
-reference.  No gradient flows through the quantile.
+``lmda`` through ordinary torch ops) and -- when a mesh requires grad, which no call site of the
+reference does -- to the mesh coordinates (pit_posatt_backward_coords).  No gradient
+flows through the quantile.
 """
 from __future__ import annotations
 
@@ -237,17 +238,24 @@ def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
     return stats[0], stats[1], stats[2], w, masked
 
 
+def meshes_need_grad(mesh_out, mesh_in) -> bool:
+    return torch.is_grad_enabled() and (mesh_out.requires_grad or mesh_in.requires_grad)
+
+
 def _meshes_are_constants(mesh_out, mesh_in) -> None:
-    # dist2att is differentiable w.r.t. the coordinates in the reference; no call site uses that and the
-    # fused kernels do not produce dX -- refuse loudly instead of returning a silent zero gradient
-    if torch.is_grad_enabled() and (mesh_out.requires_grad or mesh_in.requires_grad):
-        raise RuntimeError("position-attention: gradients w.r.t. mesh coordinates are not implemented (meshes must not require grad)")
+    # dist2att is differentiable w.r.t. the coordinates in the reference (pit.py:47); only `position_attention` produces that
+    # gradient (pit_posatt_backward_coords) -- the fused decoder tail and processor refuse loudly instead of returning a silent
+    # zero (pit.decoder / pit.processor route around them when a mesh requires grad)
+    if meshes_need_grad(mesh_out, mesh_in):
+        raise RuntimeError("fused decoder tail / processor: gradients w.r.t. mesh coordinates are only produced by position_attention")
 
 
-def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, locality: float):
+def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, locality: float, coords_grad: bool = False):
     """(mesh_out, mesh_in, stage, period, stats, entry): contiguous meshes, the validated stage, the wrap period and the
     row statistics; `entry` is the cache entry for shared meshes (None when nothing is cached)."""
-    _meshes_are_constants(mesh_out, mesh_in)
+    if not coords_grad:
+        _meshes_are_constants(mesh_out, mesh_in)
+    mesh_out, mesh_in = mesh_out.detach(), mesh_in.detach()
     capturing = mesh_in.is_cuda and torch.cuda.is_current_stream_capturing()
     cacheable = mesh_cache.enabled and mesh_in.is_cuda and mesh_in.dim() == 2
     key = mesh_cache.key(mesh_out, mesh_in, variant, locality) if cacheable else None
@@ -348,7 +356,7 @@ class _PositionAttention(torch.autograd.Function):
         scale_shape = scale.shape
         scale = scale.reshape(-1).contiguous()
         mesh_out, mesh_in, st, period, (v_min, v_lo, v_hi, w, masked), entry = prepare_meshes(
-            mesh_out, mesh_in, values, n_head, variant, float(locality))
+            mesh_out, mesh_in, values, n_head, variant, float(locality), coords_grad=True)
         plan = None if self_concat else column_plan_for(entry, st, masked)
         _check_tensor("scale", scale, st.device)
         _require(scale.numel() == st.H, f"scale must have n_head={st.H} entries, got {scale.numel()}")
@@ -399,9 +407,26 @@ class _PositionAttention(torch.autograd.Function):
                         scale.data_ptr(), C.byref(rs), rowsum.data_ptr(), d_out.data_ptr(), width, col_off,
                         int(self_concat), _ptr(d_values), _ptr(d_scale), ws.data_ptr(), ws_bytes,
                         C.byref(ctx.plan.struct) if ctx.plan is not None else None, _stream(st.device)), "pit_posatt_backward")
+            d_mesh_out = d_mesh_in = None
+            if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+                # dX (pit_posatt_backward_coords): what autograd gives the reference when a mesh requires grad
+                d_mesh_out, d_mesh_in = torch.empty_like(mesh_out), torch.empty_like(mesh_in)
+                d_period = torch.empty(1, dtype=torch.float32, device=st.device) if period is not None else None
+                with _timed("bwd_coords", st, self_concat):
+                    _cabi.check(_cabi.lib.pit_posatt_backward_coords(
+                        C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
+                        scale.data_ptr(), C.byref(rs), rowsum.data_ptr(), d_out.data_ptr(), width, col_off,
+                        d_mesh_out.data_ptr(), d_mesh_in.data_ptr(), _ptr(d_period), _stream(st.device)), "pit_posatt_backward_coords")
+                if d_period is not None:        # the wrap length is a function of mesh_in (pit.py:191-192, 248-250): chain through it
+                    with torch.enable_grad():
+                        leaf = mesh_in.detach().requires_grad_(True)
+                        (through_period,) = torch.autograd.grad(wrap_period(leaf, variant), leaf, d_period)
+                    d_mesh_in = d_mesh_in + through_period
+                d_mesh_out = d_mesh_out if ctx.needs_input_grad[2] else None
+                d_mesh_in = d_mesh_in if ctx.needs_input_grad[3] else None
         if need_scale:
             d_scale = d_scale.reshape(scale_shape)
-        return d_values, d_scale, None, None, None, None, None, None
+        return d_values, d_scale, d_mesh_out, d_mesh_in, None, None, None, None
 
 
 @torch.compiler.disable
@@ -697,6 +722,7 @@ def decoder_tail(mesh_out, mesh_in, values, scale, locality, w1, b1, w2, b2, var
     Linear is applied on the latent mesh -- Y[b,j,h,:] = W1[:, hD:(h+1)D] U[b,j,:] -- which is exact because
     position-attention is linear in its values; gradients of w1 and of the features flow through this einsum.
     """
+    _meshes_are_constants(mesh_out, mesh_in)
     B, M, D = values.shape
     H = scale.numel()
     Cw = w1.shape[0]
