@@ -38,11 +38,13 @@ def test_model_matches_reference(name, cuda_device, host_scale_map):
     finally:
         torch.set_float32_matmul_precision(prev)
     assert out.shape == g["out"].shape
-    assert rel_linf(out.detach().cpu(), t(g["out"])) <= 5e-5
-    assert abs(float(loss) - float(g["loss"])) <= 5e-5 * abs(float(g["loss"]))
-    for k, p in model.named_parameters():
-        ref = t(g["grad/" + k])
-        assert rel_linf(p.grad.cpu(), ref) <= 5e-4, k
+    errs = {k: rel_linf(p.grad.cpu(), t(g["grad/" + k])) for k, p in model.named_parameters()}
+    print(f"\nmodel_{name}: out {rel_linf(out.detach().cpu(), t(g['out'])):.2e} loss {abs(float(loss) - float(g['loss'])) / abs(float(g['loss'])):.2e} "
+          f"grads {max(errs.values()):.2e} ({max(errs, key=errs.get)})")
+    assert rel_linf(out.detach().cpu(), t(g["out"])) <= 1e-5          # the north-star bound for the fp32 / 3xTF32 path
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for k in errs:
+        assert errs[k] <= 5e-4, k
 
 
 def test_train_step_reduces_loss(cuda_device):
