@@ -39,6 +39,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+OPTIMIZER_USED = {}
 METRIC = "pit_train_samples_per_s"
 UNIT = "samples/s"
 STEP_DESC = "zero_grad+forward+RelLp loss+backward+grad allreduce(SUM)+Adam"
@@ -58,6 +59,9 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true", help="skip the other BASELINE workloads (the `workloads` dict then holds the primary one only)")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager run of baseline/_ref on the GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph")
+    ap.add_argument("--optimizer", default="auto", choices=["auto", "torch", "fused"],
+                    help="torch: torch.optim.Adam (fused kernel) after one NCCL all-reduce of the flat gradient; fused: the cross-rank SUM "
+                         "over NVLink peer memory and Adam in ONE launch (pit_allreduce_adam); auto: fused when N > 1")
     ap.add_argument("--precision", default="high", choices=["high", "highest"],
                     help="torch matmul precision for the MLP Linears (reference pit.py:2 sets 'high')")
     return ap.parse_args()
@@ -376,7 +380,22 @@ def measure_workload(name, args, rank, world, dev, detail, tf32_peak, hbm_peak):
     w = workloads.WORKLOADS[name](batch).to(dev)
     model = w.model
     use_graph = not args.no_graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph, fused=True)   # torch's single-kernel Adam
+    fused_opt = args.optimizer == "fused" or (args.optimizer == "auto" and world > 1)
+    if fused_opt:
+        from position_induced_transformer_b200.fused_optimizer import FusedAllReduceAdam
+        try:
+            opt = FusedAllReduceAdam(model.parameters(), lr=1e-3)   # cross-rank SUM over peer memory + Adam, one launch
+            ok = torch.ones(1, device=dev)
+        except Exception as ex:  # noqa: BLE001  (no peer access / symmetric memory on this box)
+            if rank == 0:
+                print(f"[bench] fused optimizer unavailable ({type(ex).__name__}: {ex}); using NCCL all-reduce + torch Adam", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)               # all ranks take the same path
+        fused_opt = bool(ok.item())
+        OPTIMIZER_USED[name] = "fused" if fused_opt else "torch"
+    if not fused_opt:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph, fused=True)   # torch's single-kernel Adam
     gen = torch.Generator().manual_seed(1234 + rank)
     n_buf = 4
     host = [w.make_batch(gen, batch) for _ in range(n_buf)]
@@ -391,13 +410,13 @@ def measure_workload(name, args, rank, world, dev, detail, tf32_peak, hbm_peak):
         # the whole step (zero grads, forward, loss, backward, all-reduce, Adam) is captured once and replayed
         step = GraphedTrainStep(list(model.parameters()), forward_loss, opt, resident[0][0], resident[0][1], world)
     else:
-        flat = FlatGradients(model.parameters(), world)
+        flat = FlatGradients(model.parameters(), 1 if fused_opt else world)
 
         def step(ins, target):
             flat.release()
             loss = forward_loss(ins, target)
             loss.backward()
-            if world > 1:
+            if world > 1 and not fused_opt:
                 flat.gather()
                 flat.all_reduce()
             opt.step()
@@ -644,6 +663,9 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": args.workload, "per_gpu_batch": batch, "global_batch": batch * world, "step": STEP_DESC,
                    "launch": "eager" if args.no_graph else "cuda_graph_replay", "parallelism": f"dp{world}", "mlp_matmul_precision": args.precision,
+                   "optimizer": ("gradient SUM over NVLink peer memory + Adam in one launch (pit_allreduce_adam)"
+                                 if OPTIMIZER_USED.get(args.workload) == "fused"
+                                 else "torch.optim.Adam(fused)" + (" after one NCCL all-reduce of the flat gradient" if world > 1 else "")),
                    "timing": f"{args.steps} steps per repeat, repeated until the timed region lasts >= {MIN_TIMED_S} s",
                    "l2": "per-step working set (activations of the decoder stage) exceeds the 126 MB L2 and input batches rotate over 4 buffers; no explicit flush"},
         "e2e": primary["e2e"], "forward_only": primary.get("forward_only"),
@@ -673,12 +695,17 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     elif args.gpus > 1:
         sys.exit("launch with torch.distributed.run for --gpus > 1")
-    try:
-        run_ours(args, rank, world, local_rank)
-    finally:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        # every rank has finished (rank 0 has printed its line): leave without tearing down NCCL communicators, captured graphs
+        # and peer-mapped buffers one by one -- their destructors wait for each other across ranks in an order Python's
+        # shutdown does not guarantee (observed: a hang at exit after a run with symmetric memory)
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -16,6 +16,7 @@
  *   pit_decoder_tail*       pit.decoder = up + de MLP, fused      pit.py:124-127, 21-26
  *   pit_tail_plan*          lambda-independent part of the mask   pit.py:136 (re-sorted every step there)
  *   pit_processor*          pit.processor, all blocks, fused      pit.py:114-122, 37-44, 21-26
+ *   pit_allreduce_adam      optimizer.step() of the scripts + the gradient SUM of a data-parallel run   train_darcy.py:115, 131
  *
  * Conventions
  *   - all tensors are fp32, contiguous, row-major, resident on the CURRENT CUDA device;
@@ -36,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 7
+#define PIT_ABI_VERSION 8
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -255,6 +256,36 @@ int pit_processor_forward(const pit_problem_t* p, int32_t n_blocks, const float*
 int pit_processor_backward(const pit_problem_t* p, int32_t n_blocks, const float* mesh, const float* period, const float* x0,
                            const float* scale, const pit_processor_block_t* blocks, int32_t linear_3xtf32, const float* saved,
                            const float* d_out, float* d_x0, float* grads, float* scratch, void* stream);
+
+/* Data-parallel optimizer step in one launch: SUM of the flat gradient over `world` ranks through peer-mapped ("symmetric")
+ * memory on NVLink, fused with torch.optim.Adam's update (no weight decay, no amsgrad: train_darcy.py:115).  The reference
+ * has no multi-GPU path; with world = 1 this is optimizer.step() alone (train_darcy.py:131).
+ *   grad[k], numel[k]  this rank's gradient tensors in parameter order (device pointers; NULL = all zeros), k < n_tensors <= 64
+ *   region[r]          rank r's symmetric region as mapped into THIS process (r < world <= 16; unused for world = 1):
+ *                      pit_allreduce_adam_region_floats(total) floats, zero-filled once before the first step on every rank
+ *                      (64 flag words, then two gradient buckets that alternate with the parity of *step)
+ *   param, exp_avg, exp_avg_sq   flat fp32 buffers of `total` = sum of ceil4(numel[k]) elements: tensor k starts at the sum of the
+ *                      rounded sizes before it, i.e. on a 16-byte boundary (parameters are views into `param`)
+ *   step               device int32: number of updates done so far (incremented by the kernel; bias corrections use step + 1)
+ *   sync               three device uint32 words, zero-initialised once: two monotone CTA counters and an error flag that is
+ *                      set to 1 if a peer's flag did not arrive within 2 s (the kernel then carries on instead of hanging)
+ *   lr                 device float (so that a scheduler can change it under a replayed CUDA graph)
+ * Every rank must call this once per step, in the same order; the kernel's CTAs wait for each other and for the peers. */
+typedef struct pit_allreduce_adam {
+  int32_t world, rank, n_tensors;
+  const float* grad[64];
+  int32_t numel[64];
+  float* region[16];
+  float* param;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int32_t* step;
+  uint32_t* sync;
+  const float* lr;
+  float beta1, beta2, eps;
+} pit_allreduce_adam_t;
+size_t pit_allreduce_adam_region_floats(int64_t total);
+int pit_allreduce_adam(const pit_allreduce_adam_t* a, void* stream);
 
 #ifdef __cplusplus
 }

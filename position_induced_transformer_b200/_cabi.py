@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 7
+ABI_VERSION = 8
 PLAN_ROWS, PLAN_COLUMNS = 0, 1
 
 EXPORTS = (
@@ -26,6 +26,7 @@ EXPORTS = (
     "pit_rel_lp_supported", "pit_rel_lp_forward", "pit_rel_lp_backward",
     "pit_processor_supported", "pit_processor_saved_floats", "pit_processor_grad_floats", "pit_processor_scratch_floats",
     "pit_processor_forward", "pit_processor_backward",
+    "pit_allreduce_adam_region_floats", "pit_allreduce_adam",
 )
 
 
@@ -46,6 +47,13 @@ class TailPlan(C.Structure):
 
 class ProcessorBlock(C.Structure):
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p)]
+
+
+class AllReduceAdam(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_tensors", C.c_int32), ("grad", C.c_void_p * 64), ("numel", C.c_int32 * 64),
+                ("region", C.c_void_p * 16), ("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("step", C.c_void_p), ("sync", C.c_void_p), ("lr", C.c_void_p), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float)]
 
 
 def _load() -> C.CDLL:
@@ -95,6 +103,9 @@ def _load() -> C.CDLL:
     lib.pit_processor_forward.argtypes = [C.POINTER(Problem), i32, f32p, f32p, f32p, f32p, C.POINTER(ProcessorBlock), i32, f32p, f32p, p]
     lib.pit_processor_backward.argtypes = [C.POINTER(Problem), i32, f32p, f32p, f32p, f32p, C.POINTER(ProcessorBlock), i32, f32p,
                                            f32p, f32p, f32p, f32p, p]
+    lib.pit_allreduce_adam_region_floats.argtypes = [i64]
+    lib.pit_allreduce_adam_region_floats.restype = C.c_size_t
+    lib.pit_allreduce_adam.argtypes = [C.POINTER(AllReduceAdam), p]
     if lib.pit_abi_version() != ABI_VERSION:
         raise ImportError(f"libpit_posatt.so ABI {lib.pit_abi_version()} != expected {ABI_VERSION}; rebuild it")
     return lib

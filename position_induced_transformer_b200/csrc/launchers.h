@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "allreduce_adam.cuh"
 #include "coord_gradient.cuh"
 #include "decoder_tail.cuh"
 #include "decoder_tail_mma.cuh"
@@ -72,6 +73,9 @@ cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cu
 // both gradient modes of a small stage (64-column tiles) in one launch
 cudaError_t dense_bwd_pair(int geo, const DenseParams& Ps, dim3 gs, const DenseParams& Pv, dim3 gv, cudaStream_t st);
 
+// tu_allreduce_adam.cu: gradient all-reduce over peer memory fused with the Adam update
+int allreduce_adam_grid(int64_t total, int sms);
+cudaError_t allreduce_adam(const AllReduceAdamParams& P, int grid, cudaStream_t st);
 // tu_coord_gradient.cu: gradient with respect to the mesh coordinates
 cudaError_t coord_gradient(int geo, const CoordGradParams& P, cudaStream_t st);
 // tu_processor.cu: the whole processor (n_blocks x [self attention + concat + MLP + GELU]) in one cluster launch per direction

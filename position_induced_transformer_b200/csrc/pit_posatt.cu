@@ -1262,4 +1262,41 @@ int pit_posatt_backward_coords(const pit_problem_t* p, const float* mesh_out, co
   return PIT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// gradient all-reduce over peer memory + Adam
+// ---------------------------------------------------------------------------------------------------------------------
+size_t pit_allreduce_adam_region_floats(int64_t total) {
+  if (total < 1) return 0;
+  const int64_t stride = (total + 3) / 4 * 4;
+  return (size_t)(pit::ARA_FLAG_WORDS + 2 * stride);
+}
+
+int pit_allreduce_adam(const pit_allreduce_adam_t* a, void* stream) {
+  if (!a) return fail(PIT_ERR_ARG, "null pointer");
+  if (a->world < 1 || a->world > pit::ARA_MAX_WORLD || a->rank < 0 || a->rank >= a->world) return fail(PIT_ERR_ARG, "allreduce_adam: bad world / rank");
+  if (a->n_tensors < 1 || a->n_tensors > pit::ARA_MAX_TENSORS) return fail(PIT_ERR_ARG, "allreduce_adam: 1..%d gradient tensors", pit::ARA_MAX_TENSORS);
+  if (!a->param || !a->exp_avg || !a->exp_avg_sq || !a->step || !a->sync || !a->lr) return fail(PIT_ERR_ARG, "null pointer");
+  pit::AllReduceAdamParams P = {};
+  P.world = a->world, P.rank = a->rank, P.n_tensors = a->n_tensors;
+  int64_t total = 0;
+  for (int k = 0; k < a->n_tensors; ++k) {
+    if (a->numel[k] < 0) return fail(PIT_ERR_ARG, "allreduce_adam: negative tensor size");
+    P.grad[k] = a->grad[k];
+    P.numel[k] = a->numel[k];
+    total += ((int64_t)a->numel[k] + 3) / 4 * 4;
+  }
+  if (total < 1) return fail(PIT_ERR_ARG, "allreduce_adam: no elements");
+  P.total = total;
+  P.stride = (total + 3) / 4 * 4;
+  for (int r = 0; r < a->world; ++r) {
+    if (a->world > 1 && !a->region[r]) return fail(PIT_ERR_ARG, "allreduce_adam: null peer region");
+    P.region[r] = a->region[r];
+  }
+  P.param = a->param, P.exp_avg = a->exp_avg, P.exp_avg_sq = a->exp_avg_sq, P.step = a->step, P.arrive = a->sync, P.lr = a->lr;
+  P.beta1 = a->beta1, P.beta2 = a->beta2, P.eps = a->eps;
+  PIT_CUDA(launch::allreduce_adam(P, launch::allreduce_adam_grid(total, sm_count()), static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
 }  // extern "C"

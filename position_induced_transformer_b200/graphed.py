@@ -23,9 +23,12 @@ class GraphedTrainStep:
     Inputs are copied into static buffers, so callers may pass fresh tensors (device or pinned host) every step.
     """
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], forward_loss: Callable, optimizer: torch.optim.Optimizer,
+    def __init__(self, params: Sequence[torch.nn.Parameter], forward_loss: Callable, optimizer,
                  example_inputs: Sequence[torch.Tensor], example_target: torch.Tensor, world_size: int = 1, warmup: int = 3):
-        self.flat = FlatGradients(params, world_size)
+        # `optimizer`: a torch optimizer (gradients are packed and summed with one NCCL all-reduce when world_size > 1), or a
+        # fused_optimizer.FusedAllReduceAdam, whose step() does the cross-rank SUM and the update in one launch
+        self.fused_reduce = hasattr(optimizer, "region_ptrs")
+        self.flat = FlatGradients(params, 1 if self.fused_reduce else world_size)
         self.forward_loss = forward_loss
         self.optimizer = optimizer
         self.static_inputs = tuple(x.clone() for x in example_inputs)
@@ -47,7 +50,7 @@ class GraphedTrainStep:
         self.flat.release()                     # grads None, as optimizer.zero_grad() leaves them: no fill, no accumulation adds
         loss = self.forward_loss(self.static_inputs, self.static_target)
         loss.backward()
-        if self.flat.world_size > 1:
+        if self.flat.world_size > 1:            # never with a FusedAllReduceAdam: its step() reduces
             self.flat.gather()                  # one multi-tensor copy into the flat bucket
             self.flat.all_reduce()
         self.optimizer.step()
