@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 8
+#define PIT_ABI_VERSION 9
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -84,6 +84,19 @@ typedef struct pit_tail_plan {
   const float* d2;
   int32_t n_tiles;
 } pit_tail_plan_t;
+
+/* Operand precision of the GLOBAL stages (locality >= 1: the dense contraction of pit.py:54-57 on tcgen05; accumulation is fp32
+ * in every mode; masked stages are always exact fp32).  Process-wide, default PIT_DENSE_FP32.
+ *   PIT_DENSE_FP32  3xTF32 products: parity with the fp32 reference (rel-Linf ~1e-6)
+ *   PIT_DENSE_TF32  single TF32 products: what torch runs the reference's einsum as under pit.py:2 ('high'); bound 1e-3
+ *   PIT_DENSE_BF16  operands rounded to BF16, fp32 accumulation; bound 5e-3
+ * The reduced modes apply to the forward product and to the value gradient; the scale gradient (a difference of large sums)
+ * always multiplies 3xTF32. */
+#define PIT_DENSE_FP32 0
+#define PIT_DENSE_TF32 1
+#define PIT_DENSE_BF16 2
+int pit_set_dense_precision(int32_t precision);
+int pit_get_dense_precision(void);
 
 /* Library identification. */
 int pit_abi_version(void);

@@ -13,11 +13,11 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 8
+ABI_VERSION = 9
 PLAN_ROWS, PLAN_COLUMNS = 0, 1
 
 EXPORTS = (
-    "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_quantile_ranks", "pit_workspace_bytes",
+    "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_set_dense_precision", "pit_get_dense_precision", "pit_quantile_ranks", "pit_workspace_bytes",
     "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward", "pit_posatt_backward_coords",
     "pit_decoder_tail_supported", "pit_decoder_tail_forward", "pit_decoder_tail_backward",
     "pit_tail_plan_workspace_bytes", "pit_tail_plan_rows", "pit_tail_plan_fill",
@@ -64,6 +64,7 @@ def _load() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     p, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
     lib.pit_abi_version.restype = C.c_int
+    lib.pit_set_dense_precision.argtypes = [i32]
     lib.pit_last_error.restype = C.c_char_p
     lib.pit_launch_count.restype = C.c_uint64
     lib.pit_quantile_ranks.argtypes = [C.c_double, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]

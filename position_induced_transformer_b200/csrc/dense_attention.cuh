@@ -69,7 +69,18 @@ struct DenseParams {
   float* d_values;  // [B,M,D]
   int add_concat;
   int split_heads;  // DVALUES: one CTA per head (grid.z = H x samples), partial sums meet in d_values (zero-initialised) by RED
+  int operand_prec; // DENSE_PREC_*: how both operands reach the tensor pipe
 };
+
+// Operand precision of the products (the accumulation is fp32 in TMEM in every case):
+//   FP32   3xTF32: hi*hi + lo*hi + hi*lo, fp32 parity (~1e-6)                                   -- the default
+//   TF32   one product on operands rounded to TF32: what the reference's einsum runs as under its own
+//          torch.set_float32_matmul_precision('high') (pit.py:2); bound 1e-3
+//   BF16   one product on operands rounded to BF16 (8 significant bits): numerically the BF16-operand / fp32-accumulate
+//          product of SURVEY 8c (bound 5e-3; a BF16 value is a TF32 value, so the kind::tf32 instruction reproduces
+//          kind::f16 exactly) -- issued on the TF32 pipe from 32-bit tiles, i.e. without the 2x rate and the halved
+//          shared-memory traffic that 16-bit operand tiles would add.
+enum : int { DENSE_PREC_FP32 = 0, DENSE_PREC_TF32 = 1, DENSE_PREC_BF16 = 2 };
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -161,6 +172,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
 // High part of the 3xTF32 split: x rounded to nearest at tf32 precision (10 explicit mantissa bits), so that the
 // residual x - hi fits the next tf32 with half the truncation error of a plain mask.
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// x rounded to the nearest BF16 value (ties to even), kept in an fp32 register
+__device__ __forceinline__ float bf16_round(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float((u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u);
+}
+// high part of an operand under the precision mode `prec`
+__device__ __forceinline__ float operand_hi(float x, int prec) { return prec == DENSE_PREC_BF16 ? bf16_round(x) : tf32_hi(x); }
 
 // Byte offset of the 16-byte chunk (row r, chunk c of 8) inside a K-major 128B-swizzled tile of 128 rows.
 __device__ __forceinline__ uint32_t a_chunk_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
@@ -246,6 +264,10 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
   const int n0 = bid.y * NV;
   const float period = P.period ? __ldg(P.period) : 0.f;
   const int sample = (MODE == DENSE_DVALUES) ? bm_dv : bm;
+  // CTA-uniform.  The scale gradient is a difference of large sums (W - (m/l) O): operand rounding shows up amplified there
+  // (measured 10 % with BF16 operands), so that mode always multiplies 3xTF32 whatever the setting.
+  const int prec = (MODE == DENSE_DSCALE) ? DENSE_PREC_FP32 : P.operand_prec;
+  const bool split = prec == DENSE_PREC_FP32;      // 3xTF32: the residual tiles are written and multiplied as well
 
   if (tid == 0) {
     for (int s = 0; s < DENSE_STAGES; ++s) {
@@ -319,21 +341,21 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
           float p = fast_exp2(fmaf(-d2, sc2, (MODE == DENSE_DVALUES) ? q.z : my_bias));
           if (MODE == DENSE_DVALUES) p *= q.w;
           lsum += p;
-          hi[e] = tf32_hi(p);
+          hi[e] = operand_hi(p, prec);
           lo[e] = p - hi[e];
           if (MODE == DENSE_DSCALE) {
             const float pd = (d2 < INFINITY) ? p * d2 : 0.f;
             msum += pd;
-            hid[e] = tf32_hi(pd);
+            hid[e] = operand_hi(pd, prec);
             lod[e] = pd - hid[e];
           }
         }
         const uint32_t off = a_chunk_offset(r, c);
         *reinterpret_cast<float4*>(stage + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(stage + L::A_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        if (split) *reinterpret_cast<float4*>(stage + L::A_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         if (MODE == DENSE_DSCALE) {
           *reinterpret_cast<float4*>(stage + 2 * L::A_BYTES + off) = make_float4(hid[0], hid[1], hid[2], hid[3]);
-          *reinterpret_cast<float4*>(stage + 3 * L::A_BYTES + off) = make_float4(lod[0], lod[1], lod[2], lod[3]);
+          if (split) *reinterpret_cast<float4*>(stage + 3 * L::A_BYTES + off) = make_float4(lod[0], lod[1], lod[2], lod[3]);
         }
       }
       fence_async_shared();
@@ -442,31 +464,46 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
     const int b = P.mesh_batched ? sample : (n_ok ? n / P.D : 0);
     const int d = P.mesh_batched ? n : n - b * P.D;
     const float* col_base = P.b_src + P.b_off + (int64_t)b * P.b_bstride + (n_ok ? d : 0);
-    for (int kb = 0; kb < n_kb; ++kb) {
-      const int s = kb % DENSE_STAGES;
-      const uint32_t use = kb / DENSE_STAGES;
+    // The value block of K block kb+1 is requested (into a second register set) BEFORE block kb is split and stored: an L2 / HBM
+    // round trip (the 1 MB value block of a sample streams through once per CTA) takes longer than one K block of MMAs, and
+    // with a single register set every K block paid it in full -- the kernel ran at the load latency, not at the tensor pipe
+    // (ncu, elasticity shape: the top stall was the first use of the loaded registers; 3xTF32 and single-product modes took
+    // the same time).
+    auto load_block = [&](int kb, float4 (&v)[PASSES]) {
       const int h = (MODE == DENSE_DVALUES) ? h_dv + kb / kb_per_head : 0;
       const int k0 = (kb % kb_per_head) * DENSE_KB;
-      // issue the global loads before waiting for the stage to drain
-      float4 v[PASSES];
 #pragma unroll
       for (int it = 0; it < PASSES; ++it) {
         const int k = k0 + krow0 + it * ROWS_PER_PASS;
-        v[it] = (n_ok && k < P.n_red) ? __ldg(reinterpret_cast<const float4*>(col_base + (int64_t)k * P.b_kstride + (int64_t)h * P.b_hstride))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[it] = (kb < n_kb && n_ok && k < P.n_red)
+                    ? __ldg(reinterpret_cast<const float4*>(col_base + (int64_t)k * P.b_kstride + (int64_t)h * P.b_hstride))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    auto store_block = [&](int kb, const float4 (&v)[PASSES]) {
+      const int s = kb % DENSE_STAGES;
+      const uint32_t use = kb / DENSE_STAGES;
       mbar_wait(&empty_bar[s], (use & 1) ^ 1);
       unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES + L::A_TILES * L::A_BYTES;
 #pragma unroll
       for (int it = 0; it < PASSES; ++it) {
-        const float4 hi = make_float4(tf32_hi(v[it].x), tf32_hi(v[it].y), tf32_hi(v[it].z), tf32_hi(v[it].w));
-        const float4 lo = make_float4(v[it].x - hi.x, v[it].y - hi.y, v[it].z - hi.z, v[it].w - hi.w);
+        const float4 hi = make_float4(operand_hi(v[it].x, prec), operand_hi(v[it].y, prec), operand_hi(v[it].z, prec), operand_hi(v[it].w, prec));
         const uint32_t off = b_chunk_offset(krow0 + it * ROWS_PER_PASS, n4);
         *reinterpret_cast<float4*>(stage + off) = hi;
-        *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = lo;
+        if (split) *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = make_float4(v[it].x - hi.x, v[it].y - hi.y, v[it].z - hi.z, v[it].w - hi.w);
       }
       fence_async_shared();
       mbar_arrive(&full_bar[s]);
+    };
+    float4 va[PASSES], vb[PASSES];
+    load_block(0, va);
+    for (int kb = 0; kb < n_kb; kb += 2) {
+      load_block(kb + 1, vb);
+      store_block(kb, va);
+      if (kb + 1 < n_kb) {
+        load_block(kb + 2, va);
+        store_block(kb + 1, vb);
+      }
     }
   } else {
     // =========================== MMA issuer ===========================
@@ -487,14 +524,18 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
           const uint64_t b_hi = umma_desc_b(b_base + kg * B_KSTEP);
           const uint64_t b_lo = umma_desc_b(b_base + L::B_BYTES + kg * B_KSTEP);
           umma_tf32(tmem_base, a_hi, b_hi, IDESC, acc);
-          umma_tf32(tmem_base, a_lo, b_hi, IDESC, 1u);
-          umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
+          if (split) {
+            umma_tf32(tmem_base, a_lo, b_hi, IDESC, 1u);
+            umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
+          }
           if (MODE == DENSE_DSCALE) {
             const uint64_t ad_hi = umma_desc(a_base + 2 * L::A_BYTES + kg * 32, 16, 1024);
             const uint64_t ad_lo = umma_desc(a_base + 3 * L::A_BYTES + kg * 32, 16, 1024);
             umma_tf32(tmem_base + NV, ad_hi, b_hi, IDESC, acc);
-            umma_tf32(tmem_base + NV, ad_lo, b_hi, IDESC, 1u);
-            umma_tf32(tmem_base + NV, ad_hi, b_lo, IDESC, 1u);
+            if (split) {
+              umma_tf32(tmem_base + NV, ad_lo, b_hi, IDESC, 1u);
+              umma_tf32(tmem_base + NV, ad_hi, b_lo, IDESC, 1u);
+            }
           }
         }
         umma_commit(&empty_bar[s]);  // the stage may be overwritten once these MMAs have read it

@@ -20,6 +20,7 @@ using pit::launch::WidePlan;
 namespace launch = pit::launch;
 
 thread_local char g_error[512] = "";
+std::atomic<int> g_dense_precision{0};   // pit_set_dense_precision: PIT_DENSE_FP32 / TF32 / BF16
 std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -317,6 +318,7 @@ bool dense_eligible(const pit_problem_t* p, const pit_rowstat_t* st) {
 pit::DenseParams dense_params(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
                               const float* scale, const pit_rowstat_t* st, int mode) {
   pit::DenseParams P{};
+  P.operand_prec = g_dense_precision.load(std::memory_order_relaxed);
   const bool dv = mode == pit::DENSE_DVALUES;
   P.mesh_own = dv ? mesh_in : mesh_out;
   P.mesh_red = dv ? mesh_out : mesh_in;
@@ -349,11 +351,23 @@ dim3 dense_grid(int mode, const pit_problem_t* p, const pit::DenseParams& P, int
   const int row_tiles = (P.n_own + pit::DENSE_ROWS - 1) / pit::DENSE_ROWS;
   const int z = mode == pit::DENSE_DVALUES ? (p->mesh_batched ? p->batch : 1) * (P.split_heads ? p->n_head : 1)
                                            : p->n_head * (p->mesh_batched ? p->batch : 1);
-  // widest tile that still gives the GPU enough CTAs; the scale-gradient mode holds two accumulators (max 128 columns each)
-  int nv = mode == pit::DENSE_DSCALE ? 128 : 256;
-  while (nv > 64 && ((int64_t)row_tiles * z * ((P.width + nv - 1) / nv) < sm_count() || nv / 2 >= P.width)) nv /= 2;
-  *nv_out = nv;
-  return dim3(row_tiles, (P.width + nv - 1) / nv, z);
+  // Column-tile width by a measured cost model.  One CTA per SM, so a launch takes ceil(CTAs / SMs) waves; the time of a CTA
+  // grows affinely with its tile width, ~ (52 + nv) units (fits the B200 timings of the elasticity, NACA and cylinder shapes
+  // at 64 / 128 / 256 columns, and does not depend on the operand precision: the kernel is bound by its producer warps, not
+  // by the tensor pipe); the scale-gradient mode generates a second operand and holds two accumulators (<= 128 columns each).
+  // E.g. NACA's value gradient: 120 CTAs of 128 columns in one wave beat 240 CTAs of 64 columns in two.
+  const bool two_acc = mode == pit::DENSE_DSCALE;
+  int best_nv = 64;
+  double best_cost = 1e300;
+  for (int nv = (two_acc ? 128 : 256); nv >= 64; nv /= 2) {
+    if (nv > 64 && nv / 2 >= P.width) continue;                       // a narrower tile already covers every column
+    const int64_t ctas = (int64_t)row_tiles * z * ((P.width + nv - 1) / nv);
+    const int64_t waves = (ctas + sm_count() - 1) / sm_count();
+    const double cost = (double)waves * (two_acc ? 83.0 + 2.0 * nv : 52.0 + nv);
+    if (cost < best_cost) best_cost = cost, best_nv = nv;
+  }
+  *nv_out = best_nv;
+  return dim3(row_tiles, (P.width + best_nv - 1) / best_nv, z);
 }
 
 cudaError_t dense_launch(int mode, int geo, const pit_problem_t* p, const pit::DenseParams& P, cudaStream_t st) {
@@ -594,6 +608,12 @@ __global__ void head_scale_bwd_kernel(const float* __restrict__ lmda, const floa
 extern "C" {
 
 int pit_abi_version(void) { return PIT_ABI_VERSION; }
+int pit_set_dense_precision(int32_t precision) {
+  if (precision < PIT_DENSE_FP32 || precision > PIT_DENSE_BF16) return fail(PIT_ERR_ARG, "dense precision must be PIT_DENSE_FP32, _TF32 or _BF16");
+  g_dense_precision.store(precision, std::memory_order_relaxed);
+  return PIT_OK;
+}
+int pit_get_dense_precision(void) { return g_dense_precision.load(std::memory_order_relaxed); }
 const char* pit_last_error(void) { return g_error; }
 uint64_t pit_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -93,6 +93,25 @@ def wrap_period(mesh_in: torch.Tensor, variant: str) -> Optional[torch.Tensor]:
     return None
 
 
+_DENSE_PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+
+
+def set_dense_precision(mode: str) -> None:
+    """Operand precision of the global (locality >= 1) stages that run on the dense tcgen05 kernel; accumulation stays fp32.
+
+    "fp32" (default)  3xTF32 products, parity with the fp32 reference to ~1e-6;
+    "tf32"            single TF32 products -- what torch runs the reference's einsum as under its own 'high' setting (pit.py:2);
+                      stated bound 1e-3;
+    "bf16"            operands rounded to BF16; stated bound 5e-3.
+    The fused processor kernel (small latent grids) and every masked stage are not affected: they stay fp32-exact."""
+    _require(mode in _DENSE_PRECISIONS, f"dense precision must be one of {sorted(_DENSE_PRECISIONS)}, got {mode!r}")
+    _cabi.check(_cabi.lib.pit_set_dense_precision(_DENSE_PRECISIONS[mode]), "pit_set_dense_precision")
+
+
+def get_dense_precision() -> str:
+    return {v: k for k, v in _DENSE_PRECISIONS.items()}[int(_cabi.lib.pit_get_dense_precision())]
+
+
 class KernelTimer:
     """Optional per-call CUDA-event timing of the C-ABI launches (used by bench.py for the roofline figures).
 

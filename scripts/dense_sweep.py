@@ -14,10 +14,12 @@ import time
 import torch
 
 sys.path.insert(0, ".")
-from position_induced_transformer_b200.posatt import position_attention, KernelTimer, set_kernel_timer  # noqa: E402
+from position_induced_transformer_b200.posatt import position_attention, KernelTimer, set_dense_precision, set_kernel_timer  # noqa: E402
 
 
-def bench(B, N, D, H, batched, reps=10):
+def bench(B, N, D, H, batched, reps=10, precision="fp32"):
+    set_dense_precision(precision)
+    terms = 3 if precision == "fp32" else 1
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
     mesh = torch.rand((B, N, 2) if batched else (N, 2), generator=g).to(dev)
@@ -40,9 +42,10 @@ def bench(B, N, D, H, batched, reps=10):
     fwd = [v for k, v in summ.items() if k[0] == "fwd"][0]["ms_avg"]
     bwd = [v for k, v in summ.items() if k[0] == "bwd"][0]["ms_avg"]
     flops = 2.0 * H * N * N * B * D
-    return {"B": B, "N": N, "D": D, "H": H, "mesh_batched": batched, "fwd_ms": fwd, "bwd_ms": bwd,
-            "fwd_TFLOPs_algorithmic": flops / fwd / 1e9, "fwd_TFLOPs_issued_tf32": 3 * flops / fwd / 1e9,
-            "bwd_TFLOPs_algorithmic": 2 * flops / bwd / 1e9, "bwd_TFLOPs_issued_tf32": 9 * flops / bwd / 1e9}
+    set_dense_precision("fp32")
+    return {"B": B, "N": N, "D": D, "H": H, "mesh_batched": batched, "operands": precision, "fwd_ms": fwd, "bwd_ms": bwd,
+            "fwd_TFLOPs_algorithmic": flops / fwd / 1e9, "fwd_TFLOPs_issued_tf32": terms * flops / fwd / 1e9,
+            "bwd_TFLOPs_algorithmic": 2 * flops / bwd / 1e9, "bwd_TFLOPs_issued_tf32": 3 * terms * flops / bwd / 1e9}
 
 
 def matmul_peak(dtype, tf32):
@@ -74,8 +77,15 @@ def main():
     ]
     if not quick:
         shapes += [(8, 1024, 64, 2, False), (16, 1024, 256, 1, False), (16, 4096, 256, 1, False), (8, 4096, 128, 2, True)]
+    import os
+    if os.environ.get("DENSE_SHAPE"):          # profiling aid: one shape, one precision (DENSE_PREC)
+        print(json.dumps(bench(*shapes[int(os.environ["DENSE_SHAPE"])], reps=3, precision=os.environ.get("DENSE_PREC", "fp32"))), flush=True)
+        return
     for s in shapes:
-        print(json.dumps(bench(*s)), flush=True)
+        for precision in ("fp32", "tf32", "bf16"):
+            if s[1] <= 256 and precision != "fp32":
+                continue        # small shared latents run the fused processor kernel in the models, not this one
+            print(json.dumps(bench(*s, precision=precision)), flush=True)
 
 
 if __name__ == "__main__":
