@@ -5,19 +5,20 @@
 // exists in HBM) and V the value features of every sample side by side (shared meshes) or of one
 // sample (per-sample meshes).  The tile loop is a warp-specialised producer/consumer pipeline:
 //
-//   warps 0-3  "generators": thread t owns tile row t; per K block it evaluates 32 weights from the
+//   warps 0-7  "generators": two threads per tile row; per K block each evaluates 16 of the 32 weights from the
 //              coordinates (exp2 with the row's known shift, so no online rescaling), splits each into a
 //              TF32 high part and an fp32 residual, and writes both as UMMA operand A (K-major,
 //              128-byte swizzle) into shared memory; it also keeps the fp32 row sum.
-//   warps 4-7  "stagers": stream the [32 x NV] value block from global memory with 128-bit loads, split
+//   warps 8-15 "stagers": stream the [32 x NV] value block from global memory with 128-bit loads, split
 //              hi/lo the same way, and store it as UMMA operand B in MN-major form.  For 32-bit operands the
 //              MN-major canonical layout is SWIZZLE_128B_BASE32B (atoms of 4 K-rows x 128 bytes, 32-byte chunks
 //              XOR-ed with the K row); with the plain SWIZZLE_128B descriptor a tf32 MN-major operand reads back
 //              as zeros (measured: scripts/probe/umma_probe.cu, modes 0/1 vs 5).  No transpose is needed.
-//   warp 8     one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=NV, K=8): hi*hi + lo*hi + hi*lo,
+//   warp 16    one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=NV, K=8): hi*hi + lo*hi + hi*lo,
 //              i.e. 3xTF32 with fp32 accumulation in TMEM (error ~2^-21, inside the 1e-5 parity budget),
 //              then tcgen05.commit's the stage back to the producers through an mbarrier.
-//   warps 0-3  epilogue: tcgen05.ld the accumulator rows out of TMEM, normalise by the row sum, store.
+//   warps 0-7  epilogue: tcgen05.ld the accumulator rows out of TMEM (the two threads of a row take half the columns each),
+//              normalise by the row sum, store.
 //
 // Operands cannot come through TMA here: both need the in-register hi/lo split (and A is computed, not
 // loaded), so the stage hand-off is mbarrier + fence.proxy.async rather than a TMA transaction count.
@@ -37,8 +38,13 @@ namespace pit {
 
 constexpr int DENSE_ROWS = 128;  // UMMA M
 constexpr int DENSE_KB = 32;     // reduction entries per K block = one 128-byte swizzle row of tf32
-constexpr int DENSE_GEN_THREADS = 128;
-constexpr int DENSE_STAGE_THREADS = 128;
+// Two generator threads per tile row (16 of the 32 weights of a K block each) and twice as many stager threads: with one warp of
+// each kind per SM sub-partition every MUFU / LDS / STS latency of the producers was exposed and the kernel ran at their pace
+// whatever the MMA count (ncu: 3xTF32 and single-product modes took the same time, issue slots 34 % busy).
+constexpr int DENSE_GEN_THREADS = 256;
+constexpr int DENSE_STAGE_THREADS = 256;
+constexpr int DENSE_GEN_WARPS = DENSE_GEN_THREADS / 32, DENSE_STAGE_WARPS = DENSE_STAGE_THREADS / 32;
+constexpr int DENSE_MMA_WARP = DENSE_GEN_WARPS + DENSE_STAGE_WARPS;
 constexpr int DENSE_THREADS = DENSE_GEN_THREADS + DENSE_STAGE_THREADS + 32;
 constexpr int DENSE_STAGES = 2;
 
@@ -231,7 +237,7 @@ struct DenseSmem {
   static constexpr int A_BYTES = DENSE_ROWS * DENSE_KB * 4;        // 16 KB
   static constexpr int B_BYTES = DENSE_KB * NV * 4;
   static constexpr int STAGE_BYTES = A_TILES * A_BYTES + 2 * B_BYTES;
-  static constexpr int TOTAL = DENSE_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 4 * 32 * 16 /*reduced-point tables*/ + 256;
+  static constexpr int TOTAL = DENSE_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + DENSE_GEN_WARPS * 32 * 16 /*reduced-point tables*/ + 256;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -247,11 +253,12 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
   __shared__ __align__(8) uint64_t full_bar[DENSE_STAGES], empty_bar[DENSE_STAGES], done_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float red[DENSE_GEN_THREADS / 32];
+  __shared__ float half_sum[2][2][DENSE_ROWS];   // [l | m][half][row]: the two generator threads of a row exchange their partial sums
 
   const uint32_t raw = smem_u32(dense_smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
   unsigned char* tiles_ptr = dense_smem_raw + (tiles - raw);
-  float4* red_pts = reinterpret_cast<float4*>(tiles_ptr + DENSE_STAGES * L::STAGE_BYTES);  // [4 warps][32] (x, y, vmin*, post)
+  float4* red_pts = reinterpret_cast<float4*>(tiles_ptr + DENSE_STAGES * L::STAGE_BYTES);  // [generator warps][32] (x, y, vmin*, post)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = bid.z;
@@ -271,13 +278,14 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
 
   if (tid == 0) {
     for (int s = 0; s < DENSE_STAGES; ++s) {
-      mbar_init(&full_bar[s], DENSE_GEN_THREADS + DENSE_STAGE_THREADS);
+      mbar_init(&full_bar[s], DENSE_GEN_WARPS + DENSE_STAGE_WARPS);   // one arrival per producer WARP (512 per-thread arrivals
+                                                                      // on one mbarrier serialise in the shared-memory atomic unit)
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  if (warp == DENSE_MMA_WARP) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -287,9 +295,10 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
   const int kb_per_head = (P.n_red + DENSE_KB - 1) / DENSE_KB;
   const int n_kb = kb_per_head * heads_in_k;
 
-  if (warp < 4) {
+  if (warp < DENSE_GEN_WARPS) {
     // =========================== generators (and epilogue) ===========================
-    const int r = tid;  // tile row
+    const int r = tid & (DENSE_ROWS - 1);  // tile row
+    const int half = tid / DENSE_ROWS;     // which 16 of the 32 weights of a K block (and which half of the epilogue columns)
     const int own = own0 + r;
     const bool own_ok = own < P.n_own;
     const float* mesh_own = P.mesh_own + (int64_t)sample * P.n_own * P.sd;
@@ -332,7 +341,8 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
       mbar_wait(&empty_bar[s], (use & 1) ^ 1);
       unsigned char* stage = tiles_ptr + s * L::STAGE_BYTES;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = half * 4 + cc;
         float hi[4], lo[4], hid[4], lod[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -358,18 +368,27 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
           if (split) *reinterpret_cast<float4*>(stage + 3 * L::A_BYTES + off) = make_float4(lod[0], lod[1], lod[2], lod[3]);
         }
       }
-      fence_async_shared();
-      mbar_arrive(&full_bar[s]);
+      fence_async_shared();      // this thread's tile writes are visible to the async proxy (the tensor pipe) ...
+      __syncwarp();              // ... for every lane of the warp ...
+      if (lane == 0) mbar_arrive(&full_bar[s]);   // ... before the warp's single arrival
     }
 
     // ------------------------------- epilogue -------------------------------
+    half_sum[0][half][r] = lsum;
+    half_sum[1][half][r] = msum;
+    asm volatile("bar.sync 1, %0;" ::"n"(DENSE_GEN_THREADS));  // generator warps only
+    lsum = half_sum[0][0][r] + half_sum[0][1][r];
+    msum = half_sum[1][0][r] + half_sum[1][1][r];
     mbar_wait(&done_bar, 0);
     tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // TMEM lanes 32 (warp % 4) .. +31 = tile rows
+    // the two threads of a row split the accumulator columns
+    constexpr int EPI_COLS = NV / 2;
+    const int c_lo = half * EPI_COLS;
     if (MODE == DENSE_FWD) {
       const float inv_l = 1.f / lsum;
-      if (own_ok && bid.y == 0) P.rowsum_out[((int64_t)sample * P.H + h_fixed) * P.N + own] = lsum;
-      for (int c0 = 0; c0 < NV; c0 += 32) {
+      if (own_ok && bid.y == 0 && half == 0) P.rowsum_out[((int64_t)sample * P.H + h_fixed) * P.N + own] = lsum;
+      for (int c0 = c_lo; c0 < c_lo + EPI_COLS; c0 += 32) {
         float v[32];
         tmem_ld32(lane_addr + c0, v);  // warp-collective: every lane takes part
         if (own_ok) {
@@ -390,7 +409,7 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
       const float l = __ldg(P.rowsum + ((int64_t)sample * P.H + h_fixed) * P.N + (own_ok ? own : 0));
       const float ratio = msum / lsum;  // m/l (lsum == l up to rounding)
       float dot = 0.f;
-      for (int c0 = 0; c0 < NV; c0 += 32) {
+      for (int c0 = c_lo; c0 < c_lo + EPI_COLS; c0 += 32) {
         float o[32], w[32];
         tmem_ld32(lane_addr + c0, o);
         tmem_ld32(lane_addr + NV + c0, w);
@@ -414,11 +433,16 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
       float v = own_ok ? -dot / l : 0.f;
       v = warp_sum(v);
       if (lane == 0) red[warp] = v;
-      asm volatile("bar.sync 1, 128;");  // generator warps only
-      if (tid == 0) atomicAdd(P.d_scale + h_fixed, red[0] + red[1] + red[2] + red[3]);
+      asm volatile("bar.sync 1, %0;" ::"n"(DENSE_GEN_THREADS));  // generator warps only
+      if (tid == 0) {
+        float total = 0.f;
+#pragma unroll
+        for (int w = 0; w < DENSE_GEN_WARPS; ++w) total += red[w];
+        atomicAdd(P.d_scale + h_fixed, total);
+      }
     } else {
       // dU[b, j, :] (+ concat pass-through)
-      for (int c0 = 0; c0 < NV; c0 += 32) {
+      for (int c0 = c_lo; c0 < c_lo + EPI_COLS; c0 += 32) {
         float v[32];
         tmem_ld32(lane_addr + c0, v);
         if (own_ok) {
@@ -447,7 +471,7 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
       }
     }
     tc_fence_before();
-  } else if (warp < 8) {
+  } else if (warp < DENSE_MMA_WARP) {
     // =========================== stagers: operand B ===========================
     // 128-bit loads along the value columns (coalesced), hi/lo split, 128-bit stores into the MN-major tile: a
     // quarter warp writes the eight 16-byte pieces of one 128-byte atom row, so the stores are conflict-free.
@@ -492,8 +516,9 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
         *reinterpret_cast<float4*>(stage + off) = hi;
         if (split) *reinterpret_cast<float4*>(stage + L::B_BYTES + off) = make_float4(v[it].x - hi.x, v[it].y - hi.y, v[it].z - hi.z, v[it].w - hi.w);
       }
-      fence_async_shared();
-      mbar_arrive(&full_bar[s]);
+      fence_async_shared();      // this thread's tile writes are visible to the async proxy (the tensor pipe) ...
+      __syncwarp();              // ... for every lane of the warp ...
+      if (lane == 0) mbar_arrive(&full_bar[s]);   // ... before the warp's single arrival
     };
     float4 va[PASSES], vb[PASSES];
     load_block(0, va);
@@ -545,7 +570,7 @@ __device__ __forceinline__ void dense_attention_body(const DenseParams& P, const
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == DENSE_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
