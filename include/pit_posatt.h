@@ -16,6 +16,7 @@
  *   pit_decoder_tail*       pit.decoder = up + de MLP, fused      pit.py:124-127, 21-26
  *   pit_tail_plan*          lambda-independent part of the mask   pit.py:136 (re-sorted every step there)
  *   pit_processor*          pit.processor, all blocks, fused      pit.py:114-122, 37-44, 21-26
+ *   pit_mlp_fused*          the encoder lift en_layer (+ GELU)     pit.py:110-111, 21-26
  *   pit_allreduce_adam      optimizer.step() of the scripts + the gradient SUM of a data-parallel run   train_darcy.py:115, 131
  *
  * Conventions
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 9
+#define PIT_ABI_VERSION 10
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -299,6 +300,18 @@ typedef struct pit_allreduce_adam {
 } pit_allreduce_adam_t;
 size_t pit_allreduce_adam_region_floats(int64_t total);
 int pit_allreduce_adam(const pit_allreduce_adam_t* a, void* stream);
+
+/* A whole kaiming_mlp with a narrow input (pit.py:21-26; the encoder lift `en_layer` of the shared-mesh models, pit.py:110-111):
+ *   out = act(W2 gelu(W1 x + b1) + b2),  act = exact GELU if act_out else identity,
+ * x [rows, in_dim] with in_dim <= 32, W1 [hid, in_dim], W2 [hid, hid], hid in {32, 64}; one launch per direction.  z1, z2
+ * [rows, hid] receive the pre-activations for the backward.  linear_3xtf32: as pit_processor_forward (the first product always
+ * runs on the fp32 pipe).  Backward: d_out [rows, hid] -> d_x [rows, in_dim] (may be NULL) and `grads`, overwritten:
+ *   d_W2 [hid, hid] | d_b2 [hid] | d_b1 [hid] | d_W1 [hid, in_dim]. */
+int pit_mlp_fused_supported(int64_t rows, int32_t in_dim, int32_t hid_dim, int32_t out_dim);
+int pit_mlp_fused_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t rows, int32_t in_dim,
+                          int32_t hid_dim, int32_t act_out, int32_t linear_3xtf32, float* z1, float* z2, float* out, void* stream);
+int pit_mlp_fused_backward(const float* x, const float* w1, const float* w2, const float* z1, const float* z2, const float* d_out, int64_t rows,
+                           int32_t in_dim, int32_t hid_dim, int32_t act_out, int32_t linear_3xtf32, float* d_x, float* grads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 9
+ABI_VERSION = 10
 PLAN_ROWS, PLAN_COLUMNS = 0, 1
 
 EXPORTS = (
@@ -27,6 +27,7 @@ EXPORTS = (
     "pit_processor_supported", "pit_processor_saved_floats", "pit_processor_grad_floats", "pit_processor_scratch_floats",
     "pit_processor_forward", "pit_processor_backward",
     "pit_allreduce_adam_region_floats", "pit_allreduce_adam",
+    "pit_mlp_fused_supported", "pit_mlp_fused_forward", "pit_mlp_fused_backward",
 )
 
 
@@ -107,6 +108,9 @@ def _load() -> C.CDLL:
     lib.pit_allreduce_adam_region_floats.argtypes = [i64]
     lib.pit_allreduce_adam_region_floats.restype = C.c_size_t
     lib.pit_allreduce_adam.argtypes = [C.POINTER(AllReduceAdam), p]
+    lib.pit_mlp_fused_supported.argtypes = [i64, i32, i32, i32]
+    lib.pit_mlp_fused_forward.argtypes = [f32p, f32p, f32p, f32p, f32p, i64, i32, i32, i32, i32, f32p, f32p, f32p, p]
+    lib.pit_mlp_fused_backward.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32, i32, i32, f32p, f32p, p]
     if lib.pit_abi_version() != ABI_VERSION:
         raise ImportError(f"libpit_posatt.so ABI {lib.pit_abi_version()} != expected {ABI_VERSION}; rebuild it")
     return lib

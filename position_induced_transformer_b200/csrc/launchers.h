@@ -13,6 +13,7 @@
 #include "dense_attention.cuh"
 #include "local_attention.cuh"
 #include "mlp_epilogue.cuh"
+#include "mlp_fused.cuh"
 #include "processor_block.cuh"
 #include "rel_lp_loss.cuh"
 #include "rowstat.cuh"
@@ -78,6 +79,8 @@ int allreduce_adam_grid(int64_t total, int sms);
 cudaError_t allreduce_adam(const AllReduceAdamParams& P, int grid, cudaStream_t st);
 // tu_coord_gradient.cu: gradient with respect to the mesh coordinates
 cudaError_t coord_gradient(int geo, const CoordGradParams& P, cudaStream_t st);
+// tu_mlp_fused.cu: Linear -> GELU -> Linear (-> GELU) with a narrow input in one launch per direction
+cudaError_t mlp_fused(bool backward, int D, bool lin3, const MlpFusedParams& P, cudaStream_t st);
 // tu_processor.cu: the whole processor (n_blocks x [self attention + concat + MLP + GELU]) in one cluster launch per direction
 constexpr int PROC_TILE_ROWS = 32;  // latent rows per CTA; the cluster of a sample has N / 32 <= 8 CTAs
 size_t processor_smem_bytes(int D, int H, int N);

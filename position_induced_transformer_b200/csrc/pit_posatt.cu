@@ -1319,4 +1319,43 @@ int pit_allreduce_adam(const pit_allreduce_adam_t* a, void* stream) {
   return PIT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// fused narrow-input MLP (the encoder lift)
+// ---------------------------------------------------------------------------------------------------------------------
+int pit_mlp_fused_supported(int64_t rows, int32_t in_dim, int32_t hid_dim, int32_t out_dim) {
+  return rows >= 1 && rows <= ((int64_t)1 << 31) - 64 && in_dim >= 1 && in_dim <= pit::MF_MAX_IN && hid_dim == out_dim && (hid_dim == 32 || hid_dim == 64) ? 1 : 0;
+}
+
+int pit_mlp_fused_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t rows, int32_t in_dim,
+                          int32_t hid_dim, int32_t act_out, int32_t linear_3xtf32, float* z1, float* z2, float* out, void* stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !z1 || !z2 || !out) return fail(PIT_ERR_ARG, "null pointer");
+  if (!pit_mlp_fused_supported(rows, in_dim, hid_dim, hid_dim)) return fail(PIT_ERR_ARG, "mlp_fused: unsupported shape (see pit_mlp_fused_supported)");
+  if ((reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(z2) | reinterpret_cast<uintptr_t>(out)) & 7u)
+    return fail(PIT_ERR_ARG, "mlp_fused: b2, z2, out must be 8-byte aligned");
+  pit::MlpFusedParams P = {};
+  P.x = x, P.w1 = w1, P.b1 = b1, P.w2 = w2, P.b2 = b2, P.z1 = z1, P.z2 = z2, P.out = out;
+  P.R = rows, P.K = in_dim, P.act_out = act_out;
+  PIT_CUDA(launch::mlp_fused(false, hid_dim, linear_3xtf32 != 0, P, static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
+int pit_mlp_fused_backward(const float* x, const float* w1, const float* w2, const float* z1, const float* z2, const float* d_out, int64_t rows,
+                           int32_t in_dim, int32_t hid_dim, int32_t act_out, int32_t linear_3xtf32, float* d_x, float* grads, void* stream) {
+  if (!x || !w1 || !w2 || !z1 || !z2 || !d_out || !grads) return fail(PIT_ERR_ARG, "null pointer");
+  if (!pit_mlp_fused_supported(rows, in_dim, hid_dim, hid_dim)) return fail(PIT_ERR_ARG, "mlp_fused: unsupported shape (see pit_mlp_fused_supported)");
+  if ((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(z1)) & 7u) return fail(PIT_ERR_ARG, "mlp_fused: grads and z1 must be 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t d = (size_t)hid_dim, k = (size_t)in_dim;
+  pit::MlpFusedParams P = {};
+  P.x = x, P.w1 = w1, P.w2 = w2, P.z1 = const_cast<float*>(z1), P.z2 = const_cast<float*>(z2), P.d_out = d_out, P.d_x = d_x;
+  P.R = rows, P.K = in_dim, P.act_out = act_out;
+  // grads: d_w2 [D,D] | d_b2 [D] | d_b1 [D] | d_w1 [D,K]  (the 8-byte aligned pieces first)
+  P.d_w2 = grads, P.d_b2 = grads + d * d, P.d_b1 = grads + d * d + d, P.d_w1 = grads + d * d + 2 * d;
+  PIT_CUDA(cudaMemsetAsync(grads, 0, (d * d + 2 * d + d * k) * sizeof(float), st));
+  PIT_CUDA(launch::mlp_fused(true, hid_dim, linear_3xtf32 != 0, P, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PIT_OK;
+}
+
 }  // extern "C"

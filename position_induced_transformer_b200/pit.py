@@ -25,7 +25,7 @@ np.random.seed(0)
 from math import pi
 
 from .posatt import (bias_act, bias_act_supported, decoder_tail, decoder_tail_supported, head_scale_cuda, meshes_need_grad,
-                     position_attention, processor_blocks, processor_supported)
+                     mlp_fused, mlp_fused_supported, position_attention, processor_blocks, processor_supported)
 
 __all__ = [
     "torch", "nn", "gelu", "np", "pi", "kaiming_mlp", "use_host_scale_map", "use_fused_decoder_tail", "use_fused_mlp_epilogue",
@@ -94,6 +94,8 @@ class kaiming_mlp(nn.Module):
         # GELU' together with the bias gradient, which autograd would run as a separate 11 us column reduction
         if (_FUSED_MLP_EPILOGUE and type(l1) is nn.Linear and type(l2) is nn.Linear and l1.bias is not None and l2.bias is not None
                 and x.is_cuda and x.dtype == torch.float32 and x.numel() > 0):
+            if mlp_fused_supported(x, l1.weight, l2.weight):       # narrow input (the encoder lift): the whole MLP in one launch
+                return mlp_fused(x, l1.weight, l1.bias, l2.weight, l2.bias, act_out)
             z1 = torch.nn.functional.linear(x, l1.weight)
             if bias_act_supported(z1, l1.bias):
                 h = bias_act(z1, l1.bias, True)

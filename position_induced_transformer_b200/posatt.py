@@ -542,6 +542,57 @@ def bias_act(z: torch.Tensor, bias: torch.Tensor, apply_gelu: bool) -> torch.Ten
 
 
 # ----------------------------------------------------------------------------------------------
+# fused narrow-input MLP: the encoder lift en_layer (+ the caller's GELU), pit.py:110-111, one launch per direction
+# ----------------------------------------------------------------------------------------------
+class _MlpFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, act_out):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
+        rows, k, d = x2.shape[0], x2.shape[1], w1.shape[0]
+        z = torch.empty((2, rows, d), dtype=torch.float32, device=x.device)
+        out = torch.empty((rows, d), dtype=torch.float32, device=x.device)
+        lin3 = _linear_3xtf32()
+        with torch.cuda.device(x.device):
+            _cabi.check(_cabi.lib.pit_mlp_fused_forward(x2.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), rows, k, d,
+                                                        int(act_out), lin3, z[0].data_ptr(), z[1].data_ptr(), out.data_ptr(),
+                                                        _stream(x.device)), "pit_mlp_fused_forward")
+        ctx.save_for_backward(x2, w1, w2, z)
+        ctx.meta = (shape, bool(act_out), lin3)
+        return out.view(*shape[:-1], d)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x2, w1, w2, z = ctx.saved_tensors
+        shape, act_out, lin3 = ctx.meta
+        rows, k, d = x2.shape[0], x2.shape[1], w1.shape[0]
+        d_out = d_out.reshape(rows, d).contiguous()
+        d_x = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        grads = torch.empty(d * d + 2 * d + d * k, dtype=torch.float32, device=x2.device)
+        with torch.cuda.device(x2.device):
+            _cabi.check(_cabi.lib.pit_mlp_fused_backward(x2.data_ptr(), w1.data_ptr(), w2.data_ptr(), z[0].data_ptr(), z[1].data_ptr(),
+                                                         d_out.data_ptr(), rows, k, d, int(act_out), lin3, _ptr(d_x), grads.data_ptr(),
+                                                         _stream(x2.device)), "pit_mlp_fused_backward")
+        d_w2, d_b2, d_b1, d_w1 = grads[:d * d].view(d, d), grads[d * d:d * d + d], grads[d * d + d:d * d + 2 * d], grads[d * d + 2 * d:].view(d, k)
+        return (None if d_x is None else d_x.view(shape)), d_w1, d_b1, d_w2, d_b2, None
+
+
+@torch.compiler.disable
+def mlp_fused_supported(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> bool:
+    """True when the one-launch MLP covers this case: float32 CUDA input of width <= 32, hidden = output width 32 or 64."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.numel() > 0 and w1.dtype == torch.float32 and w1.device == x.device
+            and w1.shape[1] == x.shape[-1] and tuple(w2.shape) == (w1.shape[0], w1.shape[0])
+            and bool(_cabi.lib.pit_mlp_fused_supported(x.numel() // x.shape[-1], x.shape[-1], w1.shape[0], w2.shape[0])))
+
+
+@torch.compiler.disable
+def mlp_fused(x, w1, b1, w2, b2, act_out: bool) -> torch.Tensor:
+    """act(W2 gelu(W1 x + b1) + b2) over the last dimension of x, act = exact GELU or identity."""
+    return _MlpFused.apply(x, w1, b1, w2, b2, bool(act_out))
+
+
+# ----------------------------------------------------------------------------------------------
 # fused processor (pit.py:114-122): every block of a shared-mesh model in one launch per direction
 # ----------------------------------------------------------------------------------------------
 def _processor_problem(mesh: torch.Tensor, x: torch.Tensor, n_head: int, variant: str) -> _cabi.Problem:
