@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PIT_ABI_VERSION 10
+#define PIT_ABI_VERSION 11
 
 #define PIT_OK 0
 #define PIT_ERR_ARG (-1)       /* bad shape / null pointer / unsupported configuration */
@@ -71,6 +71,13 @@ typedef struct pit_rowstat {
   const float* v_hi;  /* k_hi-th smallest d2                                        */
   float weight;       /* interpolation weight w of torch.quantile, in [0,1)        */
   int32_t masked;     /* 0: locality >= 1, every column kept; 1: apply the quantile mask */
+  int32_t rank_hi;    /* k_hi of pit_quantile_ranks (the 0-based rank of v_hi), or 0 if not known                       */
+  /* Neighbour lists written by pit_rowstat_lists (all three NULL if not built): for every row the columns with d2 <= v_hi -- a  */
+  /* superset of what any head keeps -- as up to 32 {column, d2} entries in ascending column order.  With them the masked stages */
+  /* over per-sample meshes never sweep the N x M pairs again.                                                                  */
+  const int16_t* nbr_idx; /* [(B),N,32]                                                       */
+  const float* nbr_d2;    /* [(B),N,32]                                                       */
+  const int32_t* nbr_cnt; /* [(B),N] true number of such columns (> 32: the list is incomplete and the stage must not use it) */
 } pit_rowstat_t;
 
 /* Tile plan of a mesh pair (described with pit_tail_plan_rows / pit_tail_plan_fill below). */
@@ -119,6 +126,11 @@ size_t pit_workspace_bytes(const pit_problem_t* p);
 int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh_in,
                 const float* period, int32_t k_lo, int32_t k_hi,
                 float* v_min, float* v_lo, float* v_hi, void* stream);
+
+/* pit_rowstat plus the neighbour lists described at pit_rowstat_t (M <= 1024); the lists come out of the sweep the order
+ * statistics need anyway. */
+int pit_rowstat_lists(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period, int32_t k_lo, int32_t k_hi,
+                      float* v_min, float* v_lo, float* v_hi, int16_t* nbr_idx, float* nbr_d2, int32_t* nbr_cnt, void* stream);
 
 /* Fused position-attention forward.
  *   values [B,M,D]; scale [H] = tan(c*(1+sin(lmda))) (pit.py:48), computed by the caller;

@@ -13,12 +13,12 @@ LIB_PATH = os.path.join(PKG, "libpit_posatt.so")
 
 PIT_EUCLID, PIT_PERIODIC1D, PIT_PERIODIC2D = 0, 1, 2
 VARIANT_CODE = {"euclid": PIT_EUCLID, "periodic1d": PIT_PERIODIC1D, "periodic2d": PIT_PERIODIC2D}
-ABI_VERSION = 10
+ABI_VERSION = 11
 PLAN_ROWS, PLAN_COLUMNS = 0, 1
 
 EXPORTS = (
     "pit_abi_version", "pit_last_error", "pit_launch_count", "pit_set_dense_precision", "pit_get_dense_precision", "pit_quantile_ranks", "pit_workspace_bytes",
-    "pit_rowstat", "pit_posatt_forward", "pit_posatt_backward", "pit_posatt_backward_coords",
+    "pit_rowstat", "pit_rowstat_lists", "pit_posatt_forward", "pit_posatt_backward", "pit_posatt_backward_coords",
     "pit_decoder_tail_supported", "pit_decoder_tail_forward", "pit_decoder_tail_backward",
     "pit_tail_plan_workspace_bytes", "pit_tail_plan_rows", "pit_tail_plan_fill",
     "pit_head_scale_forward", "pit_head_scale_backward",
@@ -38,7 +38,8 @@ class Problem(C.Structure):
 
 class RowStat(C.Structure):
     _fields_ = [("v_min", C.c_void_p), ("v_lo", C.c_void_p), ("v_hi", C.c_void_p),
-                ("weight", C.c_float), ("masked", C.c_int32)]
+                ("weight", C.c_float), ("masked", C.c_int32), ("rank_hi", C.c_int32),
+                ("nbr_idx", C.c_void_p), ("nbr_d2", C.c_void_p), ("nbr_cnt", C.c_void_p)]
 
 
 class TailPlan(C.Structure):
@@ -72,6 +73,7 @@ def _load() -> C.CDLL:
     lib.pit_workspace_bytes.argtypes = [C.POINTER(Problem)]
     lib.pit_workspace_bytes.restype = C.c_size_t
     lib.pit_rowstat.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, i32, i32, f32p, f32p, f32p, p]
+    lib.pit_rowstat_lists.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, i32, i32, f32p, f32p, f32p, p, p, p, p]
     lib.pit_posatt_forward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat),
                                        f32p, i64, i64, i32, f32p, p, C.c_size_t, C.POINTER(TailPlan), p]
     lib.pit_posatt_backward.argtypes = [C.POINTER(Problem), f32p, f32p, f32p, f32p, f32p, C.POINTER(RowStat), f32p,

@@ -17,6 +17,7 @@
 #include "processor_block.cuh"
 #include "rel_lp_loss.cuh"
 #include "rowstat.cuh"
+#include "sample_tile.cuh"
 #include "tall_attention.cuh"
 #include "wide_attention.cuh"
 
@@ -81,6 +82,9 @@ cudaError_t allreduce_adam(const AllReduceAdamParams& P, int grid, cudaStream_t 
 cudaError_t coord_gradient(int geo, const CoordGradParams& P, cudaStream_t st);
 // tu_mlp_fused.cu: Linear -> GELU -> Linear (-> GELU) with a narrow input in one launch per direction
 cudaError_t mlp_fused(bool backward, int D, bool lin3, const MlpFusedParams& P, cudaStream_t st);
+// tu_sample_tile.cu: masked stages over per-sample meshes, tiled by (sample, 64 rows)
+int sample_tile_slots(int M, int D, bool backward, int smem_optin);
+cudaError_t sample_tile(bool backward, const SampleTileParams& P, cudaStream_t st);
 // tu_processor.cu: the whole processor (n_blocks x [self attention + concat + MLP + GELU]) in one cluster launch per direction
 constexpr int PROC_TILE_ROWS = 32;  // latent rows per CTA; the cluster of a sample has N / 32 <= 8 CTAs
 size_t processor_smem_bytes(int D, int H, int N);

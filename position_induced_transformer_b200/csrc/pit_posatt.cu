@@ -639,13 +639,14 @@ size_t pit_workspace_bytes(const pit_problem_t* p) {
   return need + 256;
 }
 
-int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
-                int32_t k_lo, int32_t k_hi, float* v_min, float* v_lo, float* v_hi, void* stream) {
+static int rowstat_impl(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period, int32_t k_lo, int32_t k_hi,
+                        float* v_min, float* v_lo, float* v_hi, int16_t* nbr_idx, float* nbr_d2, int32_t* nbr_cnt, void* stream) {
   if (int rc = check_problem(p)) return rc;
   if (!mesh_out || !mesh_in || !v_min || !v_lo || !v_hi) return fail(PIT_ERR_ARG, "null pointer");
   if (p->variant != PIT_EUCLID && !period) return fail(PIT_ERR_ARG, "periodic variant needs the period pointer");
   if (k_lo < 0 || k_hi < k_lo || k_hi > k_lo + 1 || k_hi >= p->n_in)
     return fail(PIT_ERR_ARG, "ranks out of range: k_lo=%d k_hi=%d M=%d", k_lo, k_hi, p->n_in);
+  if (nbr_idx && (p->n_in > 1024 || !nbr_d2 || !nbr_cnt)) return fail(PIT_ERR_ARG, "neighbour lists need M <= 1024 and all three arrays");
   pit::RowstatParams R{};
   R.mesh_out = mesh_out;
   R.mesh_in = mesh_in;
@@ -653,6 +654,9 @@ int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh
   R.v_min = v_min;
   R.v_lo = v_lo;
   R.v_hi = v_hi;
+  R.nbr_idx = nbr_idx;
+  R.nbr_d2 = nbr_d2;
+  R.nbr_cnt = nbr_cnt;
   R.N = p->n_out;
   R.M = p->n_in;
   R.sd = p->space_dim;
@@ -664,6 +668,41 @@ int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh
   PIT_CUDA(launch::rowstat(geo_of(p), R, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
+}
+
+int pit_rowstat(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                int32_t k_lo, int32_t k_hi, float* v_min, float* v_lo, float* v_hi, void* stream) {
+  return rowstat_impl(p, mesh_out, mesh_in, period, k_lo, k_hi, v_min, v_lo, v_hi, nullptr, nullptr, nullptr, stream);
+}
+
+int pit_rowstat_lists(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period, int32_t k_lo, int32_t k_hi,
+                      float* v_min, float* v_lo, float* v_hi, int16_t* nbr_idx, float* nbr_d2, int32_t* nbr_cnt, void* stream) {
+  if (!nbr_idx) return fail(PIT_ERR_ARG, "null pointer");
+  return rowstat_impl(p, mesh_out, mesh_in, period, k_lo, k_hi, v_min, v_lo, v_hi, nbr_idx, nbr_d2, nbr_cnt, stream);
+}
+
+static bool sample_tile_eligible(const pit_problem_t* p, const pit_rowstat_t* stat, int64_t ld_out, int64_t col_off, bool backward) {
+  if (!p->mesh_batched || !stat->masked || p->n_in > 1024 || p->n_in < 1 || p->n_head > 2) return false;
+  if (p->dim % 4 != 0 || p->dim > 256 || (ld_out % 4) || (col_off % 4)) return false;
+  if (!stat->nbr_idx || !stat->nbr_d2 || !stat->nbr_cnt) return false;          // driven by the neighbour lists of pit_rowstat_lists
+  // The tiles pay off when consecutive rows share their neighbours -- an upsampling stage over an ordered mesh (NACA decoder:
+  // 11 271 rows on 728 columns).  Point clouds in arbitrary order (elasticity, N = M) touch most columns from any 64 rows: the
+  // slots overflow and the generic warp-per-row kernels are faster (measured 2x).
+  if ((int64_t)p->n_out < 4 * (int64_t)p->n_in) return false;
+  if (p->batch > 65535) return false;
+  return launch::sample_tile_slots(p->n_in, p->dim, backward, max_smem_optin()) >= 8;
+}
+
+static pit::SampleTileParams sample_tile_params(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
+                                         const float* values, const float* scale, const pit_rowstat_t* stat, bool backward) {
+  pit::SampleTileParams T = {};
+  (void)mesh_out, (void)mesh_in, (void)period;      // the distances come with the neighbour lists
+  T.values = values, T.scale = scale;
+  T.v_min = stat->v_min, T.v_lo = stat->v_lo, T.v_hi = stat->v_hi, T.weight = stat->weight;
+  T.nbr_idx = stat->nbr_idx, T.nbr_d2 = stat->nbr_d2, T.nbr_cnt = stat->nbr_cnt;
+  T.B = p->batch, T.H = p->n_head, T.N = p->n_out, T.M = p->n_in, T.D = p->dim, T.sd = p->space_dim;
+  T.n_slots = launch::sample_tile_slots(p->n_in, p->dim, backward, max_smem_optin());
+  return T;
 }
 
 int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const float* mesh_in, const float* period,
@@ -684,6 +723,13 @@ int pit_posatt_forward(const pit_problem_t* p, const float* mesh_out, const floa
   if (copy_values) {  // first D columns of the concat output (pit.py:44)
     PIT_CUDA(cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(float), values, (size_t)p->dim * sizeof(float),
                                (size_t)p->dim * sizeof(float), (size_t)p->batch * p->n_in, cudaMemcpyDeviceToDevice, st));
+  }
+  if (!copy_values && aligned16(values) && aligned16(out) && sample_tile_eligible(p, stat, ld_out, col_off, false)) {
+    pit::SampleTileParams T = sample_tile_params(p, mesh_out, mesh_in, period, values, scale, stat, false);
+    T.out = out, T.ld_out = ld_out, T.col_off = col_off, T.rowsum = rowsum;
+    PIT_CUDA(launch::sample_tile(false, T, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PIT_OK;
   }
   if (dense_eligible(p, stat)) {
     pit::DenseParams Dn = dense_params(p, mesh_out, mesh_in, period, scale, stat, pit::DENSE_FWD);
@@ -775,6 +821,17 @@ int pit_posatt_backward(const pit_problem_t* p, const float* mesh_out, const flo
   // masked cross stage, the value gradient too.  A dense self stage keeps the value gradient on the
   // column-owner kernel below (every column is touched by every row, slots would not help).
   bool values_done = d_values == nullptr, scale_done = d_scale == nullptr;
+  if (!accumulate_concat && (d_values || d_scale) && aligned16(values) && aligned16(d_out) && (!d_values || aligned16(d_values)) &&
+      sample_tile_eligible(p, stat, ld_out, col_off, true)) {
+    // per-sample meshes, masked: one pass per (sample, 64-row tile) gives both gradients
+    pit::SampleTileParams T = sample_tile_params(p, mesh_out, mesh_in, period, values, scale, stat, true);
+    T.d_out = d_out, T.ld_out = ld_out, T.col_off = col_off, T.d_values = d_values, T.d_scale = d_scale;
+    if (d_values) PIT_CUDA(cudaMemsetAsync(d_values, 0, (size_t)p->batch * p->n_in * p->dim * sizeof(float), st));
+    if (d_scale) PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
+    PIT_CUDA(launch::sample_tile(true, T, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PIT_OK;
+  }
   if (dense_eligible(p, stat)) {
     pit::DenseParams Ds{}, Dv{};
     if (d_scale) {

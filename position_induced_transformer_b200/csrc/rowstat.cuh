@@ -25,6 +25,11 @@ struct RowstatParams {
   int rows_total;  // (mesh_batched ? B : 1) * N
   int N, M, sd, mesh_batched;
   int k_lo, k_hi;
+  // optional neighbour lists (warp-per-row mapping only, M <= 1024): the columns with d2 <= v_hi of every row -- a superset of
+  // what any head keeps -- as up to 32 {column, d2} entries in ascending column order, plus the true count (may exceed 32)
+  int16_t* nbr_idx;  // [rows_total, 32] or null
+  float* nbr_d2;     // [rows_total, 32]
+  int32_t* nbr_cnt;  // [rows_total]
 };
 
 // k_lo-th and k_hi-th (k_hi in {k_lo, k_lo + 1}) smallest of the warp's 32 x RR keys (unused entries 0xffffffff).
@@ -138,6 +143,24 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
     P.v_min[row] = __uint_as_float(mn);
     P.v_lo[row] = __uint_as_float(lo);
     P.v_hi[row] = __uint_as_float(hi);
+  }
+  if (P.nbr_idx) {
+    // the keys are still in registers: one more pass compacts the candidates of the row
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool cand = key[r] <= hi;       // padding keys are 0xffffffff > hi
+      const unsigned m = __ballot_sync(FULL, cand);
+      if (cand) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (pos < 32) {
+          P.nbr_idx[(int64_t)row * 32 + pos] = (int16_t)(r * 32 + lane);
+          P.nbr_d2[(int64_t)row * 32 + pos] = __uint_as_float(key[r]);
+        }
+      }
+      cnt += __popc(m);
+    }
+    if (lane == 0) P.nbr_cnt[row] = cnt;
   }
 }
 

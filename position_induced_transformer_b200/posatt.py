@@ -250,11 +250,23 @@ def row_statistics(st: _Stage, mesh_out, mesh_in, period, locality: float):
         zeros = _zeros(st.stat_shape(), st.device)
         return zeros, zeros, zeros, w, masked
     stats = torch.empty((3,) + st.stat_shape(), dtype=torch.float32, device=st.device)
+    v_min = stats[0]
     with _timed("rowstat", st, False):
-        _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
-                                          k_lo, k_hi, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
-                                          _stream(st.device)), "pit_rowstat")
-    return stats[0], stats[1], stats[2], w, masked
+        if st.batched and st.M <= 1024 and k_hi <= _NBR_MAX_RANK and st.N >= 4 * st.M and st.D % 4 == 0 and st.D <= 256 and st.H <= 2:
+            # per-sample meshes: the sweep also leaves every row's neighbour list (columns with d2 <= v_hi), so that the masked
+            # kernels of the stage never sweep the N x M pairs again (csrc/sample_tile.cuh)
+            rows = st.rows
+            lists = (torch.empty((rows, 32), dtype=torch.int16, device=st.device), torch.empty((rows, 32), dtype=torch.float32, device=st.device),
+                     torch.empty(rows, dtype=torch.int32, device=st.device))
+            _cabi.check(_cabi.lib.pit_rowstat_lists(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), k_lo, k_hi,
+                                                    stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), lists[0].data_ptr(),
+                                                    lists[1].data_ptr(), lists[2].data_ptr(), _stream(st.device)), "pit_rowstat_lists")
+            v_min.pit_neighbour_lists = lists          # rides along with the statistics (see _rowstat_struct)
+        else:
+            _cabi.check(_cabi.lib.pit_rowstat(C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period),
+                                              k_lo, k_hi, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                                              _stream(st.device)), "pit_rowstat")
+    return v_min, stats[1], stats[2], w, masked
 
 
 def meshes_need_grad(mesh_out, mesh_in) -> bool:
@@ -351,9 +363,14 @@ def tail_plan_for(entry: Optional[_MeshEntry], st: _Stage, hidden: int) -> Optio
     return entry.tail_plan or None
 
 
-def _rowstat_struct(v_min, v_lo, v_hi, w: float, masked: bool) -> _cabi.RowStat:
+_NBR_MAX_RANK = 23      # a row's candidates (rank_hi + 1, plus ties at the cut) must fit a 32-entry neighbour list
+
+
+def _rowstat_struct(v_min, v_lo, v_hi, w: float, masked: bool, rank_hi: int = 0, lists=None) -> _cabi.RowStat:
+    lists = lists if lists is not None else getattr(v_min, "pit_neighbour_lists", None)
+    nbr = (None, None, None) if lists is None else tuple(t.data_ptr() for t in lists)
     return _cabi.RowStat(v_min.data_ptr(), v_lo.data_ptr() if masked else None, v_hi.data_ptr() if masked else None,
-                         w, int(masked))
+                         w, int(masked), int(rank_hi), *nbr)
 
 
 def column_plan_for(entry: Optional[_MeshEntry], st: _Stage, masked: bool) -> Optional[TailPlan]:
@@ -388,7 +405,9 @@ class _PositionAttention(torch.autograd.Function):
             rowsum = torch.empty(st.rowsum_shape(), dtype=torch.float32, device=st.device)
             ws_bytes = int(_cabi.lib.pit_workspace_bytes(C.byref(st.problem)))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=st.device)
-            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
+            rank_hi = _cabi.quantile_ranks(float(locality), st.M)[1] if masked else 0
+            lists = getattr(v_min, "pit_neighbour_lists", None)
+            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked, rank_hi, lists)
             with _timed("fwd", st, self_concat):
                 _cabi.check(_cabi.lib.pit_posatt_forward(
                     C.byref(st.problem), mesh_out.data_ptr(), mesh_in.data_ptr(), _ptr(period), values.data_ptr(),
@@ -396,14 +415,15 @@ class _PositionAttention(torch.autograd.Function):
                     ws.data_ptr(), ws_bytes, C.byref(plan.struct) if plan is not None else None, _stream(st.device)), "pit_posatt_forward")
         ctx.save_for_backward(values, scale, mesh_out, mesh_in, period if period is not None else scale.new_empty(0),
                               v_min, v_lo, v_hi, rowsum)
-        ctx.meta = (n_head, variant, self_concat, w, masked, scale_shape)
+        ctx.meta = (n_head, variant, self_concat, w, masked, scale_shape, rank_hi)
+        ctx.lists = lists        # neighbour lists of per-sample meshes (int16 / float32 / int32 tensors), reused by the backward
         ctx.plan = plan          # keeps the plan's tensors alive until the backward has run
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         values, scale, mesh_out, mesh_in, period, v_min, v_lo, v_hi, rowsum = ctx.saved_tensors
-        n_head, variant, self_concat, w, masked, scale_shape = ctx.meta
+        n_head, variant, self_concat, w, masked, scale_shape, rank_hi = ctx.meta
         period = period if period.numel() else None
         st = _Stage(mesh_out, mesh_in, values, n_head, variant)
         d_out = d_out.contiguous()
@@ -418,7 +438,7 @@ class _PositionAttention(torch.autograd.Function):
             col_off = st.D if self_concat else 0
             ws_bytes = int(_cabi.lib.pit_workspace_bytes(C.byref(st.problem)))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=st.device)
-            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
+            rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked, rank_hi, ctx.lists)
             if need_values or need_scale:
                 with _timed("bwd", st, self_concat):
                     _cabi.check(_cabi.lib.pit_posatt_backward(

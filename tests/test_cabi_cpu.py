@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(_cabi.EXPORTS)
     for n in names:
         assert hasattr(_cabi.lib, n), n
-    assert _cabi.lib.pit_abi_version() == _cabi.ABI_VERSION == 10
+    assert _cabi.lib.pit_abi_version() == _cabi.ABI_VERSION == 11
 
 
 @pytest.mark.parametrize("m", [2, 7, 51, 101, 120, 256, 728, 972, 1024, 1849, 2048, 4390, 177241])
