@@ -1188,11 +1188,21 @@ int pit_decoder_tail_backward(const pit_problem_t* p, const float* mesh_out, con
   P.d_w2 = d_w2;
   P.d_b2 = d_b2;
   const size_t c = (size_t)p->dim;
-  PIT_CUDA(cudaMemsetAsync(d_y, 0, (size_t)p->batch * p->n_in * p->n_head * c * sizeof(float), st));
-  PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
-  PIT_CUDA(cudaMemsetAsync(d_b1, 0, c * sizeof(float), st));
-  PIT_CUDA(cudaMemsetAsync(d_w2, 0, (size_t)out_dim * c * sizeof(float), st));
-  PIT_CUDA(cudaMemsetAsync(d_b2, 0, (size_t)out_dim * sizeof(float), st));
+  {
+    // gradient buffers that sit back to back in d_y, d_b1, d_w2, d_b2, d_scale order (each padded to a multiple of four floats, as
+    // the Python host side allocates them) are cleared with one memset node instead of five
+    auto pad = [](size_t n) { return (n + 3) / 4 * 4; };
+    const size_t n_y = (size_t)p->batch * p->n_in * p->n_head * c, n_w2 = (size_t)out_dim * c;
+    if (d_b1 == d_y + pad(n_y) && d_w2 == d_b1 + pad(c) && d_b2 == d_w2 + pad(n_w2) && d_scale == d_b2 + pad((size_t)out_dim)) {
+      PIT_CUDA(cudaMemsetAsync(d_y, 0, (pad(n_y) + pad(c) + pad(n_w2) + pad((size_t)out_dim) + (size_t)p->n_head) * sizeof(float), st));
+    } else {
+      PIT_CUDA(cudaMemsetAsync(d_y, 0, n_y * sizeof(float), st));
+      PIT_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->n_head * sizeof(float), st));
+      PIT_CUDA(cudaMemsetAsync(d_b1, 0, c * sizeof(float), st));
+      PIT_CUDA(cudaMemsetAsync(d_w2, 0, n_w2 * sizeof(float), st));
+      PIT_CUDA(cudaMemsetAsync(d_b2, 0, (size_t)out_dim * sizeof(float), st));
+    }
+  }
   if (tiled.ok)
     PIT_CUDA(launch::tail_plan_backward(geo_of(p), plan, P, tail_plan_view(tile_plan, plan.rows_per_unit, pit::TP_BWD_ROUND), st));
   else if (mma.ok)

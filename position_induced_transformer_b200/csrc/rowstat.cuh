@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
     int cnt = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
+      if (r * 32 >= P.M) break;             // warp-uniform: nothing but padding from here on
       const bool cand = key[r] <= hi;       // padding keys are 0xffffffff > hi
       const unsigned m = __ballot_sync(FULL, cand);
       if (cand) {

@@ -782,9 +782,15 @@ class _DecoderTail(torch.autograd.Function):
         st.problem.dim = Cw
         d_out = d_out.contiguous()
         with torch.cuda.device(st.device):
-            d_y = torch.empty_like(y)
-            d_scale = torch.empty(H, dtype=torch.float32, device=st.device)
-            d_b1, d_w2, d_b2 = torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+            # one allocation, gradients back to back (each piece padded to 16 bytes): the library clears them with ONE memset
+            # instead of five when it finds them contiguous
+            sizes = [y.numel(), b1.numel(), w2.numel(), b2.numel(), H]
+            offs = [0]
+            for n in sizes:
+                offs.append(offs[-1] + (n + 3) // 4 * 4)
+            flat = torch.empty(offs[-1], dtype=torch.float32, device=st.device)
+            d_y, d_b1, d_w2, d_b2, d_scale = (flat[o:o + n] for o, n in zip(offs, sizes))
+            d_y, d_b1, d_w2, d_b2 = d_y.view_as(y), d_b1.view_as(b1), d_w2.view_as(w2), d_b2.view_as(b2)
             rs = _rowstat_struct(v_min, v_lo, v_hi, w, masked)
             with _timed("tail_bwd", st, False):
                 _cabi.check(_cabi.lib.pit_decoder_tail_backward(
