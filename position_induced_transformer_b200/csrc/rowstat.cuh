@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
   mn = __reduce_min_sync(FULL, mn);
 
   uint32_t lo, hi;
-  bool done = false;
+  bool done = false, listed = false;
   // Small ranks (the locality masks keep a few dozen columns at most): shrink the problem before selecting.  The
   // (k_hi+1)-th smallest of the 32 per-lane minima is an upper bound T of the k_hi-th smallest key (those lanes hold
   // k_hi+1 distinct keys <= T), so only keys <= T can matter; a lane usually holds 0..3 of them.  They are compacted
@@ -124,17 +124,66 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
     const uint32_t bound = __shfl_sync(FULL, lm, __ffs(owner) - 1);
     if (bound != 0xffffffffu) {  // fewer than k_hi+1 lanes with a valid key: no bound, full path
       uint32_t c[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      int cr[4] = {0, 0, 0, 0};   // register index r of each candidate (its column is 32 r + lane)
       int n = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (key[r] <= bound) {
           c[3] = c[2], c[2] = c[1], c[1] = c[0], c[0] = key[r];
+          cr[3] = cr[2], cr[2] = cr[1], cr[1] = cr[0], cr[0] = r;
           ++n;
         }
       }
       if (!__any_sync(FULL, n > 4)) {
-        rowstat_select<4>(c, P.k_lo, P.k_hi, lo, hi);
-        done = true;
+        const int total = __reduce_add_sync(FULL, n);
+        if (total <= 32) {
+          // At most 32 candidates in the whole row (the usual case: k_hi + 1 of them plus a few): one per lane, ranked by
+          // counting -- 32 shuffles instead of a 32-step bit-serial selection -- and the row's neighbour list is the same set.
+          __shared__ uint32_t cand_key[4][32];
+          __shared__ int16_t cand_col[4][32];
+          const int w = threadIdx.x >> 5;
+          int before = n;   // inclusive scan of n over the lanes
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, before, o);
+            if (lane >= o) before += v;
+          }
+          before -= n;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < n) {
+              cand_key[w][before + q] = c[q];
+              cand_col[w][before + q] = (int16_t)(cr[q] * 32 + lane);
+            }
+          __syncwarp();
+          const uint32_t mine = lane < total ? cand_key[w][lane] : 0xffffffffu;
+          const int col = lane < total ? (int)cand_col[w][lane] : 0;
+          __syncwarp();       // the buffers are reused by the warp's next row
+          int rank = 0;
+          for (int l = 0; l < 32; ++l) {
+            const uint32_t other = __shfl_sync(FULL, mine, l);
+            rank += (other < mine || (other == mine && l < lane)) ? 1 : 0;
+          }
+          const unsigned at_lo = __ballot_sync(FULL, lane < total && rank == P.k_lo);
+          const unsigned at_hi = __ballot_sync(FULL, lane < total && rank == P.k_hi);
+          lo = __shfl_sync(FULL, mine, __ffs(at_lo) - 1);
+          hi = __shfl_sync(FULL, mine, __ffs(at_hi) - 1);
+          done = true;
+          if (P.nbr_idx) {
+            const bool in_list = lane < total && mine <= hi;
+            const unsigned m = __ballot_sync(FULL, in_list);
+            if (in_list) {
+              const int pos = __popc(m & ((1u << lane) - 1u));
+              P.nbr_idx[(int64_t)row * 32 + pos] = (int16_t)col;
+              P.nbr_d2[(int64_t)row * 32 + pos] = __uint_as_float(mine);
+            }
+            if (lane == 0) P.nbr_cnt[row] = __popc(m);
+            listed = true;
+          }
+        } else {
+          rowstat_select<4>(c, P.k_lo, P.k_hi, lo, hi);
+          done = true;
+        }
       }
     }
   }
@@ -144,7 +193,7 @@ __global__ void __launch_bounds__(128) rowstat_warp_kernel(const RowstatParams P
     P.v_lo[row] = __uint_as_float(lo);
     P.v_hi[row] = __uint_as_float(hi);
   }
-  if (P.nbr_idx) {
+  if (P.nbr_idx && !listed) {
     // the keys are still in registers: one more pass compacts the candidates of the row
     int cnt = 0;
 #pragma unroll
