@@ -432,6 +432,12 @@ def measure_workload(name, args, rank, world, dev, detail, tf32_peak, hbm_peak):
 
     run_resident(args.warmup)
     barrier(world)
+    if fused_opt:
+        bad = torch.tensor([float(opt.peer_timeout())], device=dev)
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)          # every rank takes the same decision
+        if float(bad) > 0:
+            raise RuntimeError("FusedAllReduceAdam: a step gave up waiting for a peer rank (2 s); the run is invalid")
     ms, timed_steps, window = timed_loop(run_resident, args.steps, world)
 
     # ---- per-kernel timing: the same step launched eagerly with CUDA events around every C-ABI call ----

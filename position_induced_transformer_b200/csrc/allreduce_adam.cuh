@@ -84,8 +84,11 @@ __device__ __forceinline__ float4 ara_load_grad(const AllReduceAdamParams& P, co
   return g;
 }
 
+// Every CTA of the launch must be resident at once (they wait for each other): two CTAs per SM by the launch bounds, and the host
+// sizes the grid from cudaOccupancyMaxActiveBlocksPerMultiprocessor.  (A first version assumed two per SM while ptxas had given the
+// kernel 158 registers -- one CTA per SM -- and deadlocked into its 2 s timeout on every step once the model needed more than 148 CTAs.)
 template <bool MULTI>   // MULTI: world > 1
-__global__ void __launch_bounds__(ARA_THREADS) allreduce_adam_kernel(const AllReduceAdamParams P) {
+__global__ void __launch_bounds__(ARA_THREADS, 2) allreduce_adam_kernel(const AllReduceAdamParams P) {
   __shared__ int64_t offs[ARA_MAX_TENSORS + 1];
   const int tid = threadIdx.x;
   const int t = *reinterpret_cast<volatile int32_t*>(P.step);   // updates done so far; every CTA reads it before anyone bumps it

@@ -76,7 +76,7 @@ cudaError_t dense(int mode, int geo, int nv, dim3 grid, const DenseParams& P, cu
 cudaError_t dense_bwd_pair(int geo, const DenseParams& Ps, dim3 gs, const DenseParams& Pv, dim3 gv, cudaStream_t st);
 
 // tu_allreduce_adam.cu: gradient all-reduce over peer memory fused with the Adam update
-int allreduce_adam_grid(int64_t total, int sms);
+int allreduce_adam_grid(int64_t total, int sms, bool multi);
 cudaError_t allreduce_adam(const AllReduceAdamParams& P, int grid, cudaStream_t st);
 // tu_coord_gradient.cu: gradient with respect to the mesh coordinates
 cudaError_t coord_gradient(int geo, const CoordGradParams& P, cudaStream_t st);

@@ -1381,7 +1381,7 @@ int pit_allreduce_adam(const pit_allreduce_adam_t* a, void* stream) {
   }
   P.param = a->param, P.exp_avg = a->exp_avg, P.exp_avg_sq = a->exp_avg_sq, P.step = a->step, P.arrive = a->sync, P.lr = a->lr;
   P.beta1 = a->beta1, P.beta2 = a->beta2, P.eps = a->eps;
-  PIT_CUDA(launch::allreduce_adam(P, launch::allreduce_adam_grid(total, sm_count()), static_cast<cudaStream_t>(stream)));
+  PIT_CUDA(launch::allreduce_adam(P, launch::allreduce_adam_grid(total, sm_count(), a->world > 1), static_cast<cudaStream_t>(stream)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return PIT_OK;
 }
