@@ -38,6 +38,24 @@ def test_single_rank_matches_torch_adam(cuda_device):
     assert all(p.data_ptr() >= opt_a.flat_param.data_ptr() for p in a.parameters())       # parameters are views of the flat buffer
 
 
+def test_single_rank_large_model_grid_is_capped(cuda_device):
+    """1.3 M parameters (the elasticity model's size): more work groups than CTAs that fit the chip at once -- the grid is capped by
+    the occupancy query and every thread takes several groups."""
+    from position_induced_transformer_b200.fused_optimizer import FusedAllReduceAdam
+    torch.manual_seed(1)
+    a = torch.nn.Sequential(torch.nn.Linear(1024, 1024), torch.nn.Linear(1024, 256)).to(cuda_device)
+    b = copy.deepcopy(a)
+    opt_a, opt_b = FusedAllReduceAdam(a.parameters(), lr=1e-3), torch.optim.Adam(b.parameters(), lr=1e-3)
+    x = torch.randn(8, 1024, device=cuda_device)
+    for _ in range(3):
+        for m, o in ((a, opt_a), (b, opt_b)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+            o.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert float((pa.detach() - pb.detach()).abs().max()) <= 2e-6 * max(1.0, float(pb.detach().abs().max()))
+
+
 def test_single_rank_step_is_graph_capturable(cuda_device):
     from position_induced_transformer_b200.fused_optimizer import FusedAllReduceAdam
     from position_induced_transformer_b200.graphed import GraphedTrainStep
