@@ -44,18 +44,19 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(PIT_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e_)); \
   } while (0)
 
-int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;  // B200
+// Device attributes are cached per device index (a process may drive GPUs of different kinds).
+int device_attr(cudaDeviceAttr attr, int slot, int fallback) {
+  static int cache[2][64];   // zero-initialised; [slot][device]
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fallback;
+  if (cache[slot][dev] == 0) {
+    int v = 0;
+    cache[slot][dev] = (cudaDeviceGetAttribute(&v, attr, dev) == cudaSuccess && v > 0) ? v : fallback;
   }
-  return cached;
+  return cache[slot][dev];
 }
+
+int sm_count() { return device_attr(cudaDevAttrMultiProcessorCount, 0, 148 /* B200 */); }
 
 int check_problem(const pit_problem_t* p) {
   if (!p) return fail(PIT_ERR_ARG, "problem is null");
@@ -150,18 +151,7 @@ pit::TailPlanDev tail_plan_view(const pit_tail_plan_t* plan, int tiles_per_cta, 
 // ---------------------------------------------------------------------------------------------
 // "tall" kernels (shared meshes, M <= 1024, H <= 2): eligibility, launch shape, dispatch
 // ---------------------------------------------------------------------------------------------
-int max_smem_optin() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 227 * 1024;
-  }
-  return cached;
-}
+int max_smem_optin() { return device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, 1, 227 * 1024); }
 
 bool tall_eligible(const pit_problem_t* p) {
   return !p->mesh_batched && p->n_in <= pit::TALL_MAX_M && p->dim % 4 == 0 && p->n_head <= pit::TALL_MAX_H;

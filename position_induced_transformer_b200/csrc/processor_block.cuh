@@ -692,21 +692,34 @@ __global__ void __launch_bounds__(PB_THREADS, 1) processor_bwd_kernel(const Proc
     }
     cluster.sync();  // every dC tile of this sample is in L2; also a CTA barrier (PS, XS, DSACC)
     if (tid < NH) atomicAdd(P.d_scale + k * NH + tid, DSACC[tid]);
-    // phase 2: transposed weights of the CTA's COLUMNS, PS[h][jt][i] = P^_h[i][row0 + jt]
-    pb_weights<NH, TR>(P.geo, N, row0, XY, period, [&](int jt, int i, int h, float d2) {
-      PS[(size_t)(h * TR + jt) * LDP + i] = pb_exp2(-d2 * sc2[h]) * IL[h * N + i];
-    });
+    // phase 2 needs the transposed weights of the CTA's COLUMNS, PT[h][jt][i] = P^_h[i][row0 + jt] = P_h[i][row0 + jt] / l_i.  The
+    // unnormalised weights are symmetric (d2 is, bit for bit), so PT[h][jt][i] = P_h[row0 + jt][i] / l_i: the tile of phase 1,
+    // P^_h[row0 + jt][i] = P_h[row0 + jt][i] / l_{row0 + jt}, rescaled in place by l_{row0 + jt} / l_i -- no second round of exponentials.
+    auto stage_dc = [&](int h) {     // dC_h of the whole sample -> XS (free since the dP products; the peers' rows come through L2)
+      for (int c = tid; c < N * (D / 4); c += PB_THREADS) {
+        const int r = c / (D / 4), q = c - r * (D / 4);
+        pb_cp16(XS + (size_t)r * LDX + 4 * q, dcs + (int64_t)r * HD + h * D + 4 * q);
+      }
+      pb_cp_commit();
+    };
+    stage_dc(0);                     // in flight while the tile is rescaled
+    for (int idx = tid; idx < NH * TR * (N / 4); idx += PB_THREADS) {
+      const int row = idx / (N / 4), i4 = (idx - row * (N / 4)) * 4;      // row = h * TR + jt
+      const int h = row / TR, jt = row - h * TR;
+      const float lrow = 1.f / IL[h * N + row0 + jt];
+      float4* pp = reinterpret_cast<float4*>(PS + (size_t)row * LDP + i4);
+      const float4 il = *reinterpret_cast<const float4*>(IL + h * N + i4);
+      float4 v = *pp;
+      v.x *= lrow * il.x, v.y *= lrow * il.y, v.z *= lrow * il.z, v.w *= lrow * il.w;
+      *pp = v;
+    }
     {
       float acc[S::MT_LIN][1][4];
       pb_zero(acc);
       const int item = warp;  // ITEMS_LIN <= PB_WARPS
       const int mg = item / (D / 8), n0 = (item - mg * (D / 8)) * 8;
       for (int h = 0; h < NH; ++h) {
-        for (int c = tid; c < N * (D / 4); c += PB_THREADS) {
-          const int r = c / (D / 4), q = c - r * (D / 4);
-          pb_cp16(XS + (size_t)r * LDX + 4 * q, dcs + (int64_t)r * HD + h * D + 4 * q);
-        }
-        pb_cp_commit();
+        if (h > 0) stage_dc(h);
         pb_cp_wait();
         __syncthreads();
         if (item < S::ITEMS_LIN) {

@@ -46,12 +46,15 @@ def test_single_rank_large_model_grid_is_capped(cuda_device):
     a = torch.nn.Sequential(torch.nn.Linear(1024, 1024), torch.nn.Linear(1024, 256)).to(cuda_device)
     b = copy.deepcopy(a)
     opt_a, opt_b = FusedAllReduceAdam(a.parameters(), lr=1e-3), torch.optim.Adam(b.parameters(), lr=1e-3)
-    x = torch.randn(8, 1024, device=cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(5)
     for _ in range(3):
-        for m, o in ((a, opt_a), (b, opt_b)):
-            o.zero_grad()
-            m(x).square().mean().backward()
-            o.step()
+        # the same gradient tensors for both (two backward passes through differently aligned parameter storage may differ in the
+        # last bit, which Adam amplifies without bound for gradients near eps)
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            grad = torch.randn(pa.shape, generator=g, device=cuda_device) * 1e-2
+            pa.grad, pb.grad = grad, grad.clone()
+        opt_a.step()
+        opt_b.step()
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert float((pa.detach() - pb.detach()).abs().max()) <= 2e-6 * max(1.0, float(pb.detach().abs().max()))
 
