@@ -70,6 +70,47 @@ def head_scale(lmda: torch.Tensor) -> torch.Tensor:
     return torch.tan(_SCALE_CONST * (1.0 + torch.sin(lmda)))
 
 
+_TALL_ROWS = 65536          # rows above which the weight gradient of a Linear is computed as a split-K batched GEMM
+_TALL_SPLITS = 256
+
+
+class _TallLinear(torch.autograd.Function):
+    """x @ W^T for a very tall x (the decoder MLP of the per-sample-mesh models runs over B * N = 225 k points, train_naca.py:60).
+
+    Forward and the input gradient are ordinary cuBLAS GEMMs.  The WEIGHT gradient dW = dZ^T x is a [out x rows] x [rows x in]
+    product with a tiny output and a huge reduction; cuBLAS' heuristic runs it on a handful of CTAs (a 64x64-tile kernel, four
+    CTAs for a 128 x 128 output: 150 us at the NACA decoder).  Here the rows are cut into 256 slices, each slice is one batch of
+    a batched GEMM (256 CTAs' worth of work), and the partial gradients are summed."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.save_for_backward(x, weight)
+        return torch.nn.functional.linear(x, weight)
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, weight = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = dz.matmul(weight)
+        if ctx.needs_input_grad[1]:
+            x2, dz2 = x.reshape(-1, x.shape[-1]), dz.reshape(-1, dz.shape[-1])
+            rows = x2.shape[0]
+            per = rows // _TALL_SPLITS
+            main = per * _TALL_SPLITS
+            dw = torch.bmm(dz2[:main].view(_TALL_SPLITS, per, -1).transpose(1, 2), x2[:main].view(_TALL_SPLITS, per, -1)).sum(0)
+            if main < rows:
+                dw = dw + dz2[main:].t().mm(x2[main:])
+        return dx, dw
+
+
+def _linear_no_bias(x, weight):
+    rows = x.numel() // max(1, x.shape[-1])
+    if rows >= _TALL_ROWS and x.is_cuda and torch.is_grad_enabled() and weight.requires_grad:
+        return _TallLinear.apply(x, weight)
+    return torch.nn.functional.linear(x, weight)
+
+
 class kaiming_mlp(nn.Module):
     """Linear -> GELU -> Linear with Kaiming-normal weights (pit.py:13-26)."""
 
@@ -96,10 +137,10 @@ class kaiming_mlp(nn.Module):
                 and x.is_cuda and x.dtype == torch.float32 and x.numel() > 0):
             if mlp_fused_supported(x, l1.weight, l2.weight):       # narrow input (the encoder lift): the whole MLP in one launch
                 return mlp_fused(x, l1.weight, l1.bias, l2.weight, l2.bias, act_out)
-            z1 = torch.nn.functional.linear(x, l1.weight)
+            z1 = _linear_no_bias(x, l1.weight)
             if bias_act_supported(z1, l1.bias):
                 h = bias_act(z1, l1.bias, True)
-                z2 = torch.nn.functional.linear(h, l2.weight)
+                z2 = _linear_no_bias(h, l2.weight)
                 if bias_act_supported(z2, l2.bias):
                     return bias_act(z2, l2.bias, act_out)
                 y = z2 + l2.bias

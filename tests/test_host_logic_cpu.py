@@ -70,3 +70,21 @@ def test_meshes_requiring_grad_are_refused():
         _meshes_are_constants(m, torch.zeros(4, 2))
     with torch.no_grad():
         _meshes_are_constants(m, m)
+
+
+def test_tall_linear_weight_gradient_by_slices_matches_plain_autograd():
+    """The split-K weight gradient of very tall Linears (pit._TallLinear) is the ordinary gradient, remainder rows included."""
+    import position_induced_transformer_b200.pit as pit_mod
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 1001, 16, generator=g, requires_grad=True)
+    w = torch.randn(5, 16, generator=g, requires_grad=True)
+    up = torch.randn(3, 1001, 5, generator=g)
+    splits = pit_mod._TALL_SPLITS
+    pit_mod._TALL_SPLITS = 8                      # 3003 rows = 8 slices of 375 + 3 remainder rows
+    try:
+        pit_mod._TallLinear.apply(x, w).backward(up)
+    finally:
+        pit_mod._TALL_SPLITS = splits
+    x2, w2 = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+    torch.nn.functional.linear(x2, w2).backward(up)
+    assert torch.allclose(x.grad, x2.grad) and torch.allclose(w.grad, w2.grad, rtol=1e-5, atol=1e-5)
