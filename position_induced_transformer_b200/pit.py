@@ -70,8 +70,8 @@ def head_scale(lmda: torch.Tensor) -> torch.Tensor:
     return torch.tan(_SCALE_CONST * (1.0 + torch.sin(lmda)))
 
 
-_TALL_ROWS = 65536          # rows above which the weight gradient of a Linear is computed as a split-K batched GEMM
-_TALL_SPLITS = 256
+_TALL_ROWS = 8192           # rows above which the weight gradient of a Linear is computed as a split-K batched GEMM
+_TALL_SPLITS = 256          # at most; one slice per 512 rows
 
 
 class _TallLinear(torch.autograd.Function):
@@ -80,7 +80,8 @@ class _TallLinear(torch.autograd.Function):
     Forward and the input gradient are ordinary cuBLAS GEMMs.  The WEIGHT gradient dW = dZ^T x is a [out x rows] x [rows x in]
     product with a tiny output and a huge reduction; cuBLAS' heuristic runs it on a handful of CTAs (a 64x64-tile kernel, four
     CTAs for a 128 x 128 output: 150 us at the NACA decoder).  Here the rows are cut into 256 slices, each slice is one batch of
-    a batched GEMM (256 CTAs' worth of work), and the partial gradients are summed."""
+    a batched GEMM (256 CTAs' worth of work), and the partial gradients are summed.  The latent-grid MLPs of the same models
+    (14 560 rows) get one slice per 512 rows: their weight gradients ran 14 us each on the same four-CTA kernel."""
 
     @staticmethod
     def forward(ctx, x, weight):
@@ -96,9 +97,10 @@ class _TallLinear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             x2, dz2 = x.reshape(-1, x.shape[-1]), dz.reshape(-1, dz.shape[-1])
             rows = x2.shape[0]
-            per = rows // _TALL_SPLITS
-            main = per * _TALL_SPLITS
-            dw = torch.bmm(dz2[:main].view(_TALL_SPLITS, per, -1).transpose(1, 2), x2[:main].view(_TALL_SPLITS, per, -1)).sum(0)
+            splits = max(2, min(_TALL_SPLITS, rows // 512))
+            per = rows // splits
+            main = per * splits
+            dw = torch.bmm(dz2[:main].view(splits, per, -1).transpose(1, 2), x2[:main].view(splits, per, -1)).sum(0)
             if main < rows:
                 dw = dw + dz2[main:].t().mm(x2[main:])
         return dx, dw
