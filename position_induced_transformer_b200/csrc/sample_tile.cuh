@@ -188,23 +188,41 @@ __global__ void __launch_bounds__(ST_THREADS) sample_tile_kernel(const SampleTil
           const int e = 4 * (lane + 32 * c);
           g[c] = e < D ? __ldg(reinterpret_cast<const float4*>(go + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // dP of every live entry: the warp reduces one dot product per entry, lane k keeps entry k's
+        // dP of every entry, sixteen at a time: each lane forms its partial dot products with all sixteen value rows (independent
+        // shared-memory loads), then a reduce-scatter butterfly (8 + 4 + 2 + 1 + 1 shuffles) leaves entry k's total on lane k --
+        // instead of one five-step warp reduction per entry
         float dp = 0.f;
-#pragma unroll 4
-        for (int k = 0; k < cnt; ++k) {
-          const int sk = __shfl_sync(FULL, slot, k), jk = __shfl_sync(FULL, j, k);
-          const float* src = sk >= 0 ? US + (size_t)sk * D : vals + (int64_t)jk * D;
-          float t = 0.f;
+        for (int base = 0; base < cnt; base += 16) {
+          float v[16];
 #pragma unroll
-          for (int c = 0; c < DC; ++c) {
-            const int e = 4 * (lane + 32 * c);
-            if (e < D) {
-              const float4 v = *reinterpret_cast<const float4*>(src + e);
-              t = fmaf(g[c].x, v.x, t), t = fmaf(g[c].y, v.y, t), t = fmaf(g[c].z, v.z, t), t = fmaf(g[c].w, v.w, t);
+          for (int kk = 0; kk < 16; ++kk) {
+            const int k = base + kk;      // warp-uniform
+            float t = 0.f;
+            if (k < cnt) {
+              const int sk = __shfl_sync(FULL, slot, k), jk = __shfl_sync(FULL, j, k);
+              const float* src = sk >= 0 ? US + (size_t)sk * D : vals + (int64_t)jk * D;
+#pragma unroll
+              for (int c = 0; c < DC; ++c) {
+                const int e = 4 * (lane + 32 * c);
+                if (e < D) {
+                  const float4 u = *reinterpret_cast<const float4*>(src + e);
+                  t = fmaf(g[c].x, u.x, t), t = fmaf(g[c].y, u.y, t), t = fmaf(g[c].z, u.z, t), t = fmaf(g[c].w, u.w, t);
+                }
+              }
+            }
+            v[kk] = t;
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+              const float keep = upper ? v[i + o] : v[i], send = upper ? v[i] : v[i + o];
+              v[i] = keep + __shfl_xor_sync(FULL, send, o);
             }
           }
-          t = warp_sum(t);
-          if (lane == k) dp = t;
+          v[0] += __shfl_xor_sync(FULL, v[0], 16);      // lanes L and L ^ 16 both hold the total of entry base + (L & 15)
+          if ((lane >> 4) == (base >> 4)) dp = v[0];
         }
         const float ph = p / l;
         const float delta = warp_sum(ph * dp);
