@@ -160,13 +160,14 @@ __global__ void __launch_bounds__(ST_THREADS) sample_tile_kernel(const SampleTil
 #pragma unroll 4
         for (int k = 0; k < cnt; ++k) {
           const float pk = __shfl_sync(FULL, p, k);
-          const int sk = __shfl_sync(FULL, slot, k), jk = __shfl_sync(FULL, j, k);
-          const float* src = sk >= 0 ? US + (size_t)sk * D : vals + (int64_t)jk * D;
+          const int sk = __shfl_sync(FULL, slot, k);       // warp-uniform: the usual case (a slot) stays on 32-bit shared addressing
+          const int jk = sk >= 0 ? 0 : __shfl_sync(FULL, j, k);
 #pragma unroll
           for (int c = 0; c < DC; ++c) {
             const int e = 4 * (lane + 32 * c);
             if (e < D) {
-              const float4 v = *reinterpret_cast<const float4*>(src + e);
+              const float4 v = sk >= 0 ? *reinterpret_cast<const float4*>(US + (sk * D + e))
+                                       : __ldg(reinterpret_cast<const float4*>(vals + (int64_t)jk * D + e));
               acc[c].x = fmaf(pk, v.x, acc[c].x), acc[c].y = fmaf(pk, v.y, acc[c].y);
               acc[c].z = fmaf(pk, v.z, acc[c].z), acc[c].w = fmaf(pk, v.w, acc[c].w);
             }
@@ -199,13 +200,14 @@ __global__ void __launch_bounds__(ST_THREADS) sample_tile_kernel(const SampleTil
             const int k = base + kk;      // warp-uniform
             float t = 0.f;
             if (k < cnt) {
-              const int sk = __shfl_sync(FULL, slot, k), jk = __shfl_sync(FULL, j, k);
-              const float* src = sk >= 0 ? US + (size_t)sk * D : vals + (int64_t)jk * D;
+              const int sk = __shfl_sync(FULL, slot, k);
+              const int jk = sk >= 0 ? 0 : __shfl_sync(FULL, j, k);
 #pragma unroll
               for (int c = 0; c < DC; ++c) {
                 const int e = 4 * (lane + 32 * c);
                 if (e < D) {
-                  const float4 u = *reinterpret_cast<const float4*>(src + e);
+                  const float4 u = sk >= 0 ? *reinterpret_cast<const float4*>(US + (sk * D + e))
+                                           : __ldg(reinterpret_cast<const float4*>(vals + (int64_t)jk * D + e));
                   t = fmaf(g[c].x, u.x, t), t = fmaf(g[c].y, u.y, t), t = fmaf(g[c].z, u.z, t), t = fmaf(g[c].w, u.w, t);
                 }
               }
@@ -232,7 +234,8 @@ __global__ void __launch_bounds__(ST_THREADS) sample_tile_kernel(const SampleTil
           for (unsigned m = live; m; m &= m - 1) {      // entries without weight add nothing: skipped (their atomics are not free)
             const int k = __ffs(m) - 1;
             const float pk = __shfl_sync(FULL, ph, k);
-            const int sk = __shfl_sync(FULL, slot, k), jk = __shfl_sync(FULL, j, k);
+            const int sk = __shfl_sync(FULL, slot, k);
+            const int jk = sk >= 0 ? 0 : __shfl_sync(FULL, j, k);
 #pragma unroll
             for (int c = 0; c < DC; ++c) {
               const int e = 4 * (lane + 32 * c);
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(ST_THREADS) sample_tile_kernel(const SampleTil
                 if (sk >= 0) {
                   // accumulator layout [slot][chunk][component][lane]: the lanes of one atomic hit consecutive banks
                   const int lw = min(32, dv - 32 * c);      // lanes that own a piece of this chunk
-                  float* dst = ACC + (size_t)sk * D + 128 * c + lane;
+                  float* dst = ACC + (sk * D + 128 * c + lane);
                   atomicAdd(dst, pk * g[c].x), atomicAdd(dst + lw, pk * g[c].y), atomicAdd(dst + 2 * lw, pk * g[c].z), atomicAdd(dst + 3 * lw, pk * g[c].w);
                 } else {
                   atomicAdd(reinterpret_cast<float4*>(P.d_values + ((int64_t)b * M + jk) * D + e),
