@@ -45,4 +45,4 @@ def test_dense_stage_precision_modes(batched, B, N, D, H, mode, cuda_device, hos
     print(f"\ndense {mode} batched={batched} N={N} D={D}: out {e_out:.2e} dU {e_dv:.2e} dlmda {e_dl:.2e}")
     assert e_out <= fwd and e_dv <= grad and e_dl <= grad_l
     if mode != "fp32":
-        assert e_out > 1e-5            # the mode really changed the arithmetic
+        assert e_out > 2e-6            # the mode really changed the arithmetic (3xTF32 sits at 2e-7, TF32 operands at 1.3e-5)
