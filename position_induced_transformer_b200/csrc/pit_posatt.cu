@@ -262,7 +262,10 @@ bool column_plan_ok(const pit_problem_t* p, const pit_tail_plan_t* plan) {
 }
 int column_plan_grid(const pit_tail_plan_t* plan) {
   const int want = (plan->n_tiles + pit::WP_WARPS - 1) / pit::WP_WARPS;   // one tile per warp ...
-  const int cap = sm_count() * 8;                                        // ... up to a full chip of resident CTAs
+  // ... up to three CTAs per SM: every CTA first builds its row (and gradient) tables, so fewer CTAs walking more tiles each
+  // beat one tile per warp (Darcy-421, 5 539 tiles: 693 CTAs 75 / 60 us backward / forward, 444 CTAs 69 / 59 us, 148 CTAs 77 / 72 us)
+  int cap = sm_count() * 3;
+  if (const char* e = getenv("PIT_WIDE_GRID")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning hook
   return want < cap ? want : cap;
 }
 
