@@ -29,3 +29,11 @@ for k in sorted(hist):
     print(f"  {k:4d}: {hist[k]:6d}  {100.0 * hist[k] / tot:5.1f} %")
 print("<= 8: %.1f %%   <= 16: %.1f %%" % (100.0 * sum(v for k, v in hist.items() if k <= 8) / tot, 100.0 * sum(v for k, v in hist.items() if k <= 16) / tot))
 # per-row candidate counts for reference
+# load balance of the backward's contiguous partition (one CTA per SM, ceil(tiles / SMs) tiles each): k-steps of 8 candidates per CTA
+import math
+sms = torch.cuda.get_device_properties(dev).multi_processor_count
+per = math.ceil(tot / sms)
+ks = [(c + 7) // 8 for c in sizes]
+loads = [sum(ks[i:i + per]) for i in range(0, tot, per)]
+print(f"backward partition: {len(loads)} CTAs x {per} tiles; k-steps per CTA min {min(loads)} mean {sum(loads) / len(loads):.1f} max {max(loads)}"
+      f" (max / mean = {max(loads) * len(loads) / sum(loads):.2f}); tiles in the last CTA: {tot - per * (len(loads) - 1)}")
