@@ -123,3 +123,43 @@ def test_star_import_surface_covers_the_reference():
         spec.loader.exec_module(mod)
         want |= {k for k in vars(mod) if not k.startswith("_")}
     assert want <= set(out), sorted(want - set(out))
+
+
+def test_round2_entry_points_validate_without_a_gpu():
+    """Shape predicates, size queries and argument checks of the round-2 entry points run on the host alone."""
+    lib = _cabi.lib
+    # fused processor: shared latent mesh of 32..256 points (a multiple of 32), width 32 / 64, <= 2 heads, <= 8 blocks
+    ok = _cabi.Problem(0, 2, 0, 8, 2, 256, 256, 64)
+    assert lib.pit_processor_supported(C.byref(ok), 4) == 1
+    for bad in (_cabi.Problem(0, 2, 1, 8, 2, 256, 256, 64),      # per-sample meshes
+                _cabi.Problem(0, 2, 0, 8, 2, 256, 256, 128),     # hidden width
+                _cabi.Problem(0, 2, 0, 8, 2, 288, 288, 64),      # more than 8 tiles of 32 rows
+                _cabi.Problem(0, 2, 0, 8, 2, 100, 100, 64),      # not a multiple of 32
+                _cabi.Problem(0, 2, 0, 8, 3, 256, 256, 64)):     # three heads
+        assert lib.pit_processor_supported(C.byref(bad), 4) == 0
+    assert lib.pit_processor_supported(C.byref(ok), 9) == 0
+    B, N, H, D, nb = 8, 256, 2, 64, 4
+    per_block = B * N * (H * D + 3 * D) + H * N
+    assert lib.pit_processor_saved_floats(C.byref(ok), nb) == nb * ((per_block + 3) // 4 * 4)
+    assert lib.pit_processor_grad_floats(C.byref(ok), nb) == nb * (D * 3 * D + D + D * D + D + H)
+    assert lib.pit_processor_scratch_floats(C.byref(ok)) == 2 * B * N * H * D
+    assert lib.pit_processor_forward(C.byref(ok), nb, None, None, None, None, None, 0, None, None, None) == -1
+    # narrow-input MLP
+    assert lib.pit_mlp_fused_supported(2048, 6, 64, 64) == 1 and lib.pit_mlp_fused_supported(2048, 33, 64, 64) == 0
+    assert lib.pit_mlp_fused_supported(2048, 6, 128, 128) == 0 and lib.pit_mlp_fused_supported(2048, 6, 64, 32) == 0
+    # operand precision of the dense stages: a process-wide setting with a range check
+    assert lib.pit_get_dense_precision() == 0
+    assert lib.pit_set_dense_precision(2) == 0 and lib.pit_get_dense_precision() == 2
+    assert lib.pit_set_dense_precision(7) == -1 and lib.pit_get_dense_precision() == 2
+    assert lib.pit_set_dense_precision(0) == 0
+    # peer-memory optimizer step: region size and argument checks
+    assert lib.pit_allreduce_adam_region_floats(79004) == 64 + 2 * 79004
+    assert lib.pit_allreduce_adam_region_floats(5) == 64 + 2 * 8
+    a = _cabi.AllReduceAdam()
+    a.world, a.rank, a.n_tensors = 17, 0, 1
+    assert lib.pit_allreduce_adam(C.byref(a), None) == -1 and b"world" in lib.pit_last_error()
+    a.world, a.n_tensors = 2, 65
+    assert lib.pit_allreduce_adam(C.byref(a), None) == -1
+    # neighbour lists need all three arrays and M <= 1024
+    big = _cabi.Problem(0, 2, 1, 2, 1, 64, 2048, 8)
+    assert lib.pit_rowstat_lists(C.byref(big), 1, 1, None, 3, 4, 1, 1, 1, 1, 1, 1, None) == -1
