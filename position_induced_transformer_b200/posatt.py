@@ -286,9 +286,12 @@ def prepare_meshes(mesh_out, mesh_in, values, n_head: int, variant: str, localit
     row statistics; `entry` is the cache entry for shared meshes (None when nothing is cached)."""
     if not coords_grad:
         _meshes_are_constants(mesh_out, mesh_in)
+    # a mesh that is being trained changes between steps -- possibly through a kernel that does not bump its version counter
+    # (fused_optimizer.FusedAllReduceAdam writes the flat parameter buffer directly) -- so its statistics are never cached
+    learnable = mesh_out.requires_grad or mesh_in.requires_grad
     mesh_out, mesh_in = mesh_out.detach(), mesh_in.detach()
     capturing = mesh_in.is_cuda and torch.cuda.is_current_stream_capturing()
-    cacheable = mesh_cache.enabled and mesh_in.is_cuda and mesh_in.dim() == 2
+    cacheable = mesh_cache.enabled and mesh_in.is_cuda and mesh_in.dim() == 2 and not learnable
     key = mesh_cache.key(mesh_out, mesh_in, variant, locality) if cacheable else None
     hit = mesh_cache.get(key) if key is not None else None
     if hit is not None:
